@@ -1,0 +1,234 @@
+/*
+ * rbx.h -- C ABI of the B200-native rigid-body hot path (librbx.so).
+ *
+ * This is the drop-in boundary for the one hot path of
+ * dineshadepu/rigid_body_2d_3d_pysph: one time step of the rigid-body scheme
+ * (SURVEY.md section 3.3, 8a).  The reference has no FFI of its own -- PySPH
+ * transpiles the Python Equation / IntegratorStep methods to Cython at run
+ * time -- so each entry point below names the reference method(s) whose
+ * generated loop it replaces (paths relative to /root/reference/code/).
+ *
+ * Conventions
+ *  - Every pointer inside the descriptor structs is a DEVICE pointer owned by
+ *    the caller (torch tensors on the Python side).  The library allocates
+ *    nothing persistent and keeps no global state.
+ *  - All calls are asynchronous on the given stream (a cudaStream_t passed as
+ *    void*), capture-safe (no syncs, no allocations), and re-entrant across
+ *    streams and devices.
+ *  - Return value: RBX_OK or a negative RbxError; no C++ exception crosses
+ *    the ABI.  Device-side capacity problems (slot table full, neighbour
+ *    list full, grid too large) are OR-ed into the device status word
+ *    RbxScene.status, which the host reads at a sync point of its choosing.
+ *  - Real data are FP64, ids int32, exactly as PySPH's `double` / `int`.
+ */
+#ifndef RBX_H_
+#define RBX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RBX_VERSION 100 /* 0.1.0 */
+
+typedef enum {
+  RBX_OK = 0,
+  RBX_ERR_INVALID = -1,   /* bad argument / null pointer / size */
+  RBX_ERR_WORKSPACE = -2, /* workspace too small */
+  RBX_ERR_LAUNCH = -3,    /* CUDA launch error (cudaGetLastError) */
+  RBX_ERR_NO_DEVICE = -4
+} RbxError;
+
+/* bits of the device status word */
+#define RBX_STATUS_SLOT_OVERFLOW 1u  /* > RBX_MAX_KEYS bodies touch a particle */
+#define RBX_STATUS_HIST_OVERFLOW 2u  /* > ks simultaneous contacts            */
+#define RBX_STATUS_LIST_OVERFLOW 4u  /* per-particle neighbour list full       */
+#define RBX_STATUS_GRID_COARSENED 8u /* cell size enlarged to fit cap_cells    */
+#define RBX_STATUS_LVC_OVERFLOW 16u  /* LVC tangential history `limit` hit     */
+
+#define RBX_MAX_KEYS 8   /* distinct source bodies per particle per step */
+
+/* Uniform grid description, written on the device by rbx_cells_build. */
+typedef struct {
+  double x0, y0, z0;  /* origin = min corner of the binned points */
+  double cell;        /* cell edge >= radius_scale * h_max        */
+  double inv_cell;
+  int32_t nx, ny, nz;
+  int32_t ncells;     /* nx*ny*nz <= cap_cells                    */
+  int32_t npoints;    /* points binned                            */
+  int32_t pad_;
+} RbxGridInfo;
+
+/* A set of points to bin: the particles `index[k]` (k < n) of the scene's
+ * global SoA arrays, or particles 0..n-1 when index is NULL. */
+typedef struct {
+  int32_t n;
+  int32_t pad_;
+  const int32_t *index;
+  const double *x, *y, *z, *h;
+  const int32_t *dem_id;
+} RbxPoints;
+
+/* Cell list, caller-allocated.  After rbx_cells_build:
+ *   cell_start[c] .. cell_start[c+1]  = sorted range of cell c
+ *   (c = (cz*ny + cy)*nx + cx, x fastest), ascending global index inside a
+ *   cell (deterministic);  gidx/sx/sy/sz/sh/sdem = sorted SoA copies.      */
+typedef struct {
+  int32_t cap_cells;   /* cell_start has cap_cells + 1 entries */
+  int32_t cap_points;
+  RbxGridInfo *info;   /* device */
+  int32_t *cell_start; /* [cap_cells + 1] */
+  int32_t *cell_of;    /* [cap_points] scratch: cell id per binned point */
+  int32_t *rank;       /* [cap_points] scratch: arrival rank inside cell */
+  int32_t *gidx;       /* [cap_points] sorted -> global particle index   */
+  double *sx, *sy, *sz, *sh; /* [cap_points] sorted copies              */
+  int32_t *sdem;       /* [cap_points] */
+} RbxCells;
+
+/* The scene: global SoA over all particles (rigid-body particles first,
+ * static boundary particles after), per-body state in the reference's own
+ * layout (3*b+j, 9*b+j), and the sparse contact history.                  */
+typedef struct {
+  int32_t n_total;   /* all particles                                     */
+  int32_t n_rigid;   /* destination (rigid-body) particles: [0, n_rigid)  */
+  int32_t n_bodies;  /* rigid bodies (global numbering across arrays)     */
+  int32_t n_chunks;  /* work items: <= 128 consecutive particles of 1 body */
+  int32_t dim;       /* kernel dimension (2 or 3)                          */
+  int32_t ks;        /* history slots per particle                         */
+  int32_t eta_mode;  /* 0: none, 1: dense table rows, 2: uniform scalar    */
+  int32_t planar;    /* 1: GTVFRigidBody2DStep semantics                   */
+  /* per particle [n_total] */
+  double *x, *y, *z, *u, *v, *w;
+  const double *h, *m, *rho;
+  const int32_t *dem_id;
+  /* per rigid particle [n_rigid] */
+  double *fx, *fy, *fz;
+  const double *dx0, *dy0, *dz0;
+  const int32_t *body;        /* global body index                       */
+  const int32_t *is_boundary; /* may be NULL: no normal rotation         */
+  const double *normal0;      /* stride 3, may be NULL                   */
+  double *normal;             /* stride 3, may be NULL                   */
+  /* work items */
+  const int32_t *chunk_start; /* [n_chunks + 1] particle ranges          */
+  const int32_t *chunk_body;  /* [n_chunks]                              */
+  const int32_t *body_chunk;  /* [n_bodies + 1] chunk ranges per body    */
+  double *chunk_ft;           /* [n_chunks * 6] partial force, torque    */
+  /* per body */
+  const double *total_mass, *izz, *spacing0; /* [n_bodies]               */
+  double *xcm, *vcm, *ang_mom, *omega;       /* [3 n_bodies]             */
+  double *force, *torque;                    /* [3 n_bodies]             */
+  double *R, *R_prev;                        /* [9 n_bodies]             */
+  const double *iinv_b;                      /* [9 n_bodies]             */
+  double *iinv_g;                            /* [9 n_bodies]             */
+  double *xcm0, *vcm0, *ang_mom0, *R0;       /* RK2 saved state          */
+  /* damping table (rigid_body_common.py:925): eta_mode 1 -> value
+   * eta[eta_row[body] + source_dem_id]; eta_mode 2 -> eta[0]            */
+  const double *eta;
+  const int64_t *eta_row;
+  /* sparse history, slot-major [ks][n_rigid]; key = source dem_id, -1 end */
+  const int32_t *hist_key_in;
+  const double *hist_dlt_in, *hist_fn_in; /* [3][ks][n_rigid] */
+  int32_t *hist_key_out;
+  double *hist_dlt_out, *hist_fn_out;
+  /* device status word + counters: [0] gated in-range pairs, [1] active
+   * (in-contact) slots, [2] candidate distance tests                     */
+  uint32_t *status;
+  unsigned long long *counters;
+} RbxScene;
+
+typedef struct {
+  double radius_scale; /* 3.0 for QuinticSpline */
+  double kr, kf, fric_coeff;
+  double gx, gy, gz;
+  double dt;
+  double reach;     /* radius_scale * h_max over ALL arrays = minimum cell edge */
+  double h_uniform; /* > 0: every particle has this h (skips the h loads)  */
+} RbxParams;
+
+/* Optional per-slot diagnostics of one contact evaluation, slot-major
+ * [RBX_MAX_KEYS][n_rigid]; any pointer may be NULL.  Used by parity tests
+ * to rebuild the reference's dense (particle, body) slot arrays.          */
+typedef struct {
+  int32_t *key;     /* source dem_id, -1 = unused                        */
+  int32_t *closest; /* global index of the closest source particle       */
+  double *nx, *ny, *nz, *dist, *overlap, *ftx, *fty, *ftz;
+} RbxDiag;
+
+int rbx_version(void);
+const char *rbx_strerror(int code);
+/* sizeof(RbxGridInfo, RbxPoints, RbxCells, RbxScene, RbxParams, RbxDiag) for
+ * which = 0..5: lets a binding check its struct mirrors. */
+size_t rbx_sizeof(int which);
+
+/* Scratch bytes needed by rbx_cells_build for a cell list of this capacity. */
+size_t rbx_cells_workspace_bytes(int32_t cap_cells, int32_t cap_points);
+
+/* [upstream] NNPS.update (LinkedListNNPS binning).
+ * Counting-sort cell-list build: bounds -> cell ids + histogram -> prefix
+ * scan -> scatter -> per-cell index sort -> gather of the sorted SoA.
+ * min_cell = radius_scale * h_max over all arrays.                       */
+int rbx_cells_build(const RbxPoints *pts, const RbxCells *cells,
+                    double min_cell, uint32_t *status, void *workspace,
+                    size_t workspace_bytes, void *stream);
+/* (min_cell = RbxParams.reach) */
+
+/* [upstream] NNPS.get_nearest_particles: for every point of `dst`, the
+ * source particles j of the cell list with r2 < (k h_i)^2 or r2 < (k h_j)^2.
+ * Parity mode.  With idx == NULL only counts[i] is written; otherwise
+ * offsets[i] (exclusive scan of counts, made by the caller) places row i.  */
+int rbx_pairs_dump(const RbxPoints *dst, const RbxCells *cells,
+                   double radius_scale, int32_t *counts,
+                   const int64_t *offsets, int32_t *idx, void *stream);
+
+/* ComputeContactForceNormals + ComputeContactForceDistanceAndClosestPoint +
+ * BodyForce + ComputeContactForce (rigid_body_common.py:631-1032, :115-125),
+ * fused, with sparse slots, plus the per-chunk partial sums of
+ * SumUpExternalForces (:128-175).  Reads history *_in, writes *_out.       */
+int rbx_contact_mofidi(const RbxScene *scene, const RbxCells *cells,
+                       const RbxParams *params, const RbxDiag *diag,
+                       void *stream);
+
+/* SumUpExternalForces.reduce (rigid_body_common.py:128-175): chunk partials
+ * -> force[3nb], torque[3nb] in a fixed order (deterministic).             */
+int rbx_reduce_bodies(const RbxScene *scene, void *stream);
+
+/* GTVFRigidBody{3D,2D}Step.py_stage1 / py_stage3 (rigid_body_3d.py:41-60,
+ * 171-190; rigid_body_2d.py:41-55, 157-170): half kick of vcm, ang_mom,
+ * omega.                                                                    */
+int rbx_gtvf_kick(const RbxScene *scene, double dt, void *stream);
+
+/* GTVFRigidBody{3D,2D}Step.py_stage2 + normalize_R_orientation
+ * (rigid_body_3d.py:97-132, rigid_body_common.py:178-203): drift of xcm, R
+ * (R_prev keeps the pre-drift orientation), inertia update.                */
+int rbx_gtvf_drift(const RbxScene *scene, double dt, void *stream);
+
+/* stage1/stage3 (velocities, rigid_body_3d.py:62-95, 192-225) and stage2
+ * (positions + boundary normals, :134-169) of the body particles.
+ * flags: RBX_POSE_* below.                                                 */
+#define RBX_POSE_POS 1       /* x,y,z = xcm + R r0                       */
+#define RBX_POSE_VEL 2       /* u,v,w = vcm + omega x (R r0)             */
+#define RBX_POSE_VEL_PREV 4  /* velocities use R_prev (stage1 fused after drift) */
+#define RBX_POSE_NORMALS 8   /* rotate normal0 -> normal where is_boundary */
+int rbx_pose_particles(const RbxScene *scene, int flags, void *stream);
+
+/* RK2RigidBody3DStep (rigid_body_3d.py:406-575): stage 0 = py_initialize
+ * (fix_q7 != 0 saves ang_mom0 of every body), 1 and 2 =
+ * py_stage1 / py_stage2.  Particle update: rbx_pose_particles(POS|VEL).    */
+int rbx_rk2_stage(const RbxScene *scene, int stage, double dt, int fix_q7,
+                  void *stream);
+
+/* Whole GTVF step [upstream GTVFIntegrator.one_timestep, SURVEY App. C-6]:
+ * kick, drift, pose, cells_build, contact, reduce, kick, velocities.
+ * `src` = the source points (contact_force_is_boundary == 1) to bin.
+ * flags: bit0 = skip the final particle-velocity write (state not observed) */
+int rbx_gtvf_step(const RbxScene *scene, const RbxPoints *src,
+                  const RbxCells *cells, const RbxParams *params,
+                  void *workspace, size_t workspace_bytes, int flags,
+                  void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RBX_H_ */

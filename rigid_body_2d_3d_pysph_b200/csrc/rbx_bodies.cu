@@ -1,0 +1,306 @@
+// Per-body kernels: force/torque reduction and the rigid steppers, plus the
+// per-particle pose kernel.  One warp per body for the reduction (lanes
+// stride over the body's chunk partials, fixed shuffle tree => deterministic);
+// the 3x3 algebra of a body is done by lane 0 (a few hundred flops).
+//
+//   SumUpExternalForces.reduce        rigid_body_common.py:128-175
+//   GTVFRigidBody3DStep.py_stage1/3   rigid_body_3d.py:41-60, 171-190
+//   GTVFRigidBody3DStep.py_stage2     rigid_body_3d.py:97-132
+//   normalize_R_orientation           rigid_body_common.py:178-203
+//   GTVFRigidBody2DStep               rigid_body_2d.py:40-205
+//   RK2RigidBody3DStep                rigid_body_3d.py:406-575
+//   stage1/2/3 particle updates       rigid_body_3d.py:62-95, 134-169, 192-225
+#include "rbx_common.cuh"
+
+namespace {
+
+__device__ __forceinline__ void matvec3(const double *A, const double *b, double *o) {
+#pragma unroll
+  for (int r = 0; r < 3; r++) o[r] = A[3 * r] * b[0] + A[3 * r + 1] * b[1] + A[3 * r + 2] * b[2];
+}
+__device__ __forceinline__ void matmul3(const double *A, const double *B, double *C) {
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+      C[3 * r + c] = A[3 * r] * B[c] + A[3 * r + 1] * B[3 + c] + A[3 * r + 2] * B[6 + c];
+}
+
+// classical Gram-Schmidt on the columns of the row-major 3x3 `o`
+__device__ void normalize_R(double *o) {
+  double a1[3] = {o[0], o[3], o[6]}, a2[3] = {o[1], o[4], o[7]}, a3[3] = {o[2], o[5], o[8]};
+  double na1 = sqrt(a1[0] * a1[0] + a1[1] * a1[1] + a1[2] * a1[2]);
+  double b1[3] = {a1[0] / na1, a1[1] / na1, a1[2] / na1};
+  double d12 = b1[0] * a2[0] + b1[1] * a2[1] + b1[2] * a2[2];
+  double b2[3] = {a2[0] - d12 * b1[0], a2[1] - d12 * b1[1], a2[2] - d12 * b1[2]};
+  double nb2 = sqrt(b2[0] * b2[0] + b2[1] * b2[1] + b2[2] * b2[2]);
+#pragma unroll
+  for (int k = 0; k < 3; k++) b2[k] /= nb2;
+  double d13 = b1[0] * a3[0] + b1[1] * a3[1] + b1[2] * a3[2];
+  double d23 = b2[0] * a3[0] + b2[1] * a3[1] + b2[2] * a3[2];
+  double b3[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) b3[k] = a3[k] - d13 * b1[k] - d23 * b2[k];
+  double nb3 = sqrt(b3[0] * b3[0] + b3[1] * b3[1] + b3[2] * b3[2]);
+#pragma unroll
+  for (int k = 0; k < 3; k++) b3[k] /= nb3;
+  o[0] = b1[0]; o[3] = b1[1]; o[6] = b1[2];
+  o[1] = b2[0]; o[4] = b2[1]; o[7] = b2[2];
+  o[2] = b3[0]; o[5] = b3[1]; o[8] = b3[2];
+}
+
+// R <- GS(Rbase + h [omega]x R);  Iinv_g <- R Iinv_b R^T (skipped if planar)
+__device__ void rotate_body(double *R, const double *Rbase, const double *om, double h,
+                            const double *iinv_b, double *iinv_g) {
+  double W[9] = {0, -om[2], om[1], om[2], 0, -om[0], -om[1], om[0], 0};
+  double Rl[9], rd[9];
+#pragma unroll
+  for (int k = 0; k < 9; k++) Rl[k] = R[k];
+  matmul3(W, Rl, rd);
+#pragma unroll
+  for (int k = 0; k < 9; k++) Rl[k] = Rbase[k] + rd[k] * h;
+  normalize_R(Rl);
+#pragma unroll
+  for (int k = 0; k < 9; k++) R[k] = Rl[k];
+  if (iinv_g) {
+    double Rt[9] = {Rl[0], Rl[3], Rl[6], Rl[1], Rl[4], Rl[7], Rl[2], Rl[5], Rl[8]};
+    double Ib[9], tmp[9], out[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) Ib[k] = iinv_b[k];
+    matmul3(Rl, Ib, tmp);
+    matmul3(tmp, Rt, out);
+#pragma unroll
+    for (int k = 0; k < 9; k++) iinv_g[k] = out[k];
+  }
+}
+
+__device__ __forceinline__ void kick_body(const RbxScene &S, int b, double dtb2) {
+  const int i3 = 3 * b, i9 = 9 * b;
+  const double M = S.total_mass[b];
+  if (S.planar) {
+#pragma unroll
+    for (int j = 0; j < 2; j++) S.vcm[i3 + j] = S.vcm[i3 + j] + (dtb2 * S.force[i3 + j] / M);
+    S.omega[i3 + 2] += dtb2 * S.torque[i3 + 2] / S.izz[b];
+  } else {
+    double L[3], om[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      S.vcm[i3 + j] = S.vcm[i3 + j] + (dtb2 * S.force[i3 + j] / M);
+      L[j] = S.ang_mom[i3 + j] + (dtb2 * S.torque[i3 + j]);
+      S.ang_mom[i3 + j] = L[j];
+    }
+    matvec3(S.iinv_g + i9, L, om);
+#pragma unroll
+    for (int j = 0; j < 3; j++) S.omega[i3 + j] = om[j];
+  }
+}
+
+__device__ __forceinline__ void drift_body(const RbxScene &S, int b, double dt) {
+  const int i3 = 3 * b, i9 = 9 * b;
+  const int nd = S.planar ? 2 : 3;
+  for (int j = 0; j < nd; j++) S.xcm[i3 + j] = S.xcm[i3 + j] + dt * S.vcm[i3 + j];
+  double om[3] = {S.omega[i3], S.omega[i3 + 1], S.omega[i3 + 2]};
+  if (S.R_prev) {
+#pragma unroll
+    for (int k = 0; k < 9; k++) S.R_prev[i9 + k] = S.R[i9 + k];
+  }
+  rotate_body(S.R + i9, S.R + i9, om, dt, S.iinv_b + i9, S.planar ? nullptr : S.iinv_g + i9);
+}
+
+// mode bits: 1 = reduce chunk partials, 2 = kick, 4 = drift, 8 = kick before drift
+// order executed: [reduce] [kick (post)] [kick (pre)] [drift]
+__global__ void k_bodies(RbxScene S, int mode, double dt) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= S.n_bodies) return;
+  const int b = warp;
+  if (mode & 1) {
+    double v6[6] = {0, 0, 0, 0, 0, 0};
+    const int c0 = S.body_chunk[b], c1 = S.body_chunk[b + 1];
+    for (int c = c0 + lane; c < c1; c += 32) {
+#pragma unroll
+      for (int a = 0; a < 6; a++) v6[a] += S.chunk_ft[(size_t)c * 6 + a];
+    }
+#pragma unroll
+    for (int a = 0; a < 6; a++) v6[a] = rbx_warp_sum(v6[a]);
+    if (lane == 0) {
+#pragma unroll
+      for (int a = 0; a < 3; a++) { S.force[3 * b + a] = v6[a]; S.torque[3 * b + a] = v6[3 + a]; }
+    }
+  }
+  if (lane != 0) return;
+  if (mode & 2) kick_body(S, b, dt / 2.);
+  if (mode & 8) kick_body(S, b, dt / 2.);
+  if (mode & 4) drift_body(S, b, dt);
+}
+
+__global__ void k_rk2(RbxScene S, int stage, double dt, int fix_q7) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= S.n_bodies) return;
+  const int i3 = 3 * b, i9 = 9 * b;
+  if (stage == 0) {  // py_initialize :407-419
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      S.xcm0[i3 + j] = S.xcm[i3 + j];
+      S.vcm0[i3 + j] = S.vcm[i3 + j];
+      if (fix_q7 || b == 0) S.ang_mom0[i3 + j] = S.ang_mom[i3 + j];
+    }
+#pragma unroll
+    for (int k = 0; k < 9; k++) S.R0[i9 + k] = S.R[i9 + k];
+    return;
+  }
+  const double h = (stage == 1) ? dt / 2. : dt;
+  const double M = S.total_mass[b];
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    S.xcm[i3 + j] = S.xcm0[i3 + j] + h * S.vcm[i3 + j];
+    S.vcm[i3 + j] = S.vcm0[i3 + j] + h * S.force[i3 + j] / M;
+  }
+  double om[3] = {S.omega[i3], S.omega[i3 + 1], S.omega[i3 + 2]};
+  rotate_body(S.R + i9, S.R0 + i9, om, h, S.iinv_b + i9, S.iinv_g + i9);
+  double L[3];
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    L[j] = S.ang_mom0[i3 + j] + (h * S.torque[i3 + j]);
+    S.ang_mom[i3 + j] = L[j];
+  }
+  matvec3(S.iinv_g + i9, L, om);
+#pragma unroll
+  for (int j = 0; j < 3; j++) S.omega[i3 + j] = om[j];
+}
+
+__global__ void k_pose(RbxScene S, int flags) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= S.n_rigid) return;
+  const int b = S.body[p];
+  const int i9 = 9 * b, i3 = 3 * b;
+  const double x0 = S.dx0[p], y0 = S.dy0[p], z0 = S.dz0[p];
+  double R[9];
+#pragma unroll
+  for (int k = 0; k < 9; k++) R[k] = S.R[i9 + k];
+  if (flags & RBX_POSE_VEL) {
+    double Rv[9];
+    if (flags & RBX_POSE_VEL_PREV) {
+#pragma unroll
+      for (int k = 0; k < 9; k++) Rv[k] = S.R_prev[i9 + k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 9; k++) Rv[k] = R[k];
+    }
+    const double dx = (Rv[0] * x0 + Rv[1] * y0 + Rv[2] * z0);
+    const double dy = (Rv[3] * x0 + Rv[4] * y0 + Rv[5] * z0);
+    const double dz = (Rv[6] * x0 + Rv[7] * y0 + Rv[8] * z0);
+    const double o0 = S.omega[i3], o1 = S.omega[i3 + 1], o2 = S.omega[i3 + 2];
+    const double du = o1 * dz - o2 * dy;
+    const double dv = o2 * dx - o0 * dz;
+    const double dw = o0 * dy - o1 * dx;
+    S.u[p] = S.vcm[i3] + du;
+    S.v[p] = S.vcm[i3 + 1] + dv;
+    S.w[p] = S.vcm[i3 + 2] + dw;
+  }
+  if (flags & RBX_POSE_POS) {
+    const double dx = (R[0] * x0 + R[1] * y0 + R[2] * z0);
+    const double dy = (R[3] * x0 + R[4] * y0 + R[5] * z0);
+    const double dz = (R[6] * x0 + R[7] * y0 + R[8] * z0);
+    S.x[p] = S.xcm[i3] + dx;
+    S.y[p] = S.xcm[i3 + 1] + dy;
+    S.z[p] = S.xcm[i3 + 2] + dz;
+    if ((flags & RBX_POSE_NORMALS) && S.normal && S.is_boundary && S.is_boundary[p] == 1) {
+      const double n0 = S.normal0[3 * p], n1 = S.normal0[3 * p + 1], n2 = S.normal0[3 * p + 2];
+      S.normal[3 * p] = (R[0] * n0 + R[1] * n1 + R[2] * n2);
+      S.normal[3 * p + 1] = (R[3] * n0 + R[4] * n1 + R[5] * n2);
+      S.normal[3 * p + 2] = (R[6] * n0 + R[7] * n1 + R[8] * n2);
+    }
+  }
+}
+
+int launch_bodies(const RbxScene *S, int mode, double dt, cudaStream_t st) {
+  if (S->n_bodies <= 0) return RBX_OK;
+  const int T = 128;
+  k_bodies<<<rbx_blocks((long long)S->n_bodies * 32, T), T, 0, st>>>(*S, mode, dt);
+  RBX_CHECK_LAUNCH();
+  return RBX_OK;
+}
+
+}  // namespace
+
+extern "C" int rbx_reduce_bodies(const RbxScene *scene, void *stream) {
+  if (!scene) return RBX_ERR_INVALID;
+  return launch_bodies(scene, 1, 0., (cudaStream_t)stream);
+}
+
+extern "C" int rbx_gtvf_kick(const RbxScene *scene, double dt, void *stream) {
+  if (!scene) return RBX_ERR_INVALID;
+  return launch_bodies(scene, 2, dt, (cudaStream_t)stream);
+}
+
+extern "C" int rbx_gtvf_drift(const RbxScene *scene, double dt, void *stream) {
+  if (!scene) return RBX_ERR_INVALID;
+  return launch_bodies(scene, 4, dt, (cudaStream_t)stream);
+}
+
+extern "C" int rbx_pose_particles(const RbxScene *scene, int flags, void *stream) {
+  if (!scene) return RBX_ERR_INVALID;
+  if (scene->n_rigid <= 0) return RBX_OK;
+  if ((flags & RBX_POSE_VEL_PREV) && !scene->R_prev) return RBX_ERR_INVALID;
+  k_pose<<<rbx_blocks(scene->n_rigid, 256), 256, 0, (cudaStream_t)stream>>>(*scene, flags);
+  RBX_CHECK_LAUNCH();
+  return RBX_OK;
+}
+
+extern "C" int rbx_rk2_stage(const RbxScene *scene, int stage, double dt, int fix_q7,
+                             void *stream) {
+  if (!scene || stage < 0 || stage > 2) return RBX_ERR_INVALID;
+  if (!scene->xcm0 || !scene->vcm0 || !scene->ang_mom0 || !scene->R0) return RBX_ERR_INVALID;
+  if (scene->n_bodies <= 0) return RBX_OK;
+  k_rk2<<<rbx_blocks(scene->n_bodies, 128), 128, 0, (cudaStream_t)stream>>>(*scene, stage, dt, fix_q7);
+  RBX_CHECK_LAUNCH();
+  return RBX_OK;
+}
+
+// Whole GTVF step: kick + drift (one body launch), positions + stage-1
+// velocities (one particle launch), cell list, contact, reduce + kick (one
+// body launch), stage-3 velocities.
+extern "C" int rbx_gtvf_step(const RbxScene *scene, const RbxPoints *src, const RbxCells *cells,
+                             const RbxParams *params, void *workspace, size_t workspace_bytes,
+                             int flags, void *stream) {
+  if (!scene || !src || !cells || !params) return RBX_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if ((rc = launch_bodies(scene, 8 | 4, params->dt, st))) return rc;
+  if ((rc = rbx_pose_particles(scene, RBX_POSE_POS | RBX_POSE_VEL | RBX_POSE_VEL_PREV |
+                                          RBX_POSE_NORMALS, stream))) return rc;
+  if ((rc = rbx_cells_build(src, cells, params->reach, scene->status, workspace,
+                            workspace_bytes, stream))) return rc;
+  if ((rc = rbx_contact_mofidi(scene, cells, params, nullptr, stream))) return rc;
+  if ((rc = launch_bodies(scene, 1 | 2, params->dt, st))) return rc;
+  if (!(flags & 1))
+    if ((rc = rbx_pose_particles(scene, RBX_POSE_VEL, stream))) return rc;
+  return RBX_OK;
+}
+
+extern "C" int rbx_version(void) { return RBX_VERSION; }
+
+extern "C" const char *rbx_strerror(int code) {
+  switch (code) {
+    case RBX_OK: return "ok";
+    case RBX_ERR_INVALID: return "invalid argument";
+    case RBX_ERR_WORKSPACE: return "workspace too small";
+    case RBX_ERR_LAUNCH: return "CUDA launch failed";
+    case RBX_ERR_NO_DEVICE: return "no CUDA device";
+    default: return "unknown error";
+  }
+}
+
+// sizeof of the ABI structs, so that bindings can verify their mirrors
+extern "C" size_t rbx_sizeof(int which) {
+  switch (which) {
+    case 0: return sizeof(RbxGridInfo);
+    case 1: return sizeof(RbxPoints);
+    case 2: return sizeof(RbxCells);
+    case 3: return sizeof(RbxScene);
+    case 4: return sizeof(RbxParams);
+    case 5: return sizeof(RbxDiag);
+    default: return 0;
+  }
+}

@@ -1,0 +1,86 @@
+// Shared device helpers for librbx (sm_100a).  See include/rbx.h for the ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rbx.h"
+
+#define RBX_CHUNK 128     // threads per CTA = max particles per work item
+#define RBX_TILE 768      // staged source particles per shared-memory tile
+#define RBX_LISTCAP 160   // in-range gated neighbours kept per particle
+
+#define RBX_CHECK_LAUNCH()                                   \
+  do {                                                       \
+    if (cudaPeekAtLastError() != cudaSuccess) {              \
+      cudaGetLastError();                                    \
+      return RBX_ERR_LAUNCH;                                 \
+    }                                                        \
+  } while (0)
+
+static inline int rbx_blocks(long long n, int threads) {
+  long long b = (n + threads - 1) / threads;
+  return (int)(b < 1 ? 1 : b);
+}
+
+// ---- ordered-uint64 encoding of doubles, for atomicMin/atomicMax ----
+__device__ __forceinline__ unsigned long long rbx_ord(double v) {
+  unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double rbx_unord(unsigned long long k) {
+  unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+  return __longlong_as_double((long long)b);
+}
+
+// r2 = dx*dx + dy*dy + dz*dz with every product and sum rounded separately
+// (no FMA contraction): the neighbour predicate has to be bit-exact against
+// the CPU path (SURVEY.md App. C-1, section 7 "Bit-exact neighbour sets").
+__device__ __forceinline__ double rbx_r2(double dx, double dy, double dz) {
+  return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+// (k h)^2 = k*k*h*h evaluated left to right
+__device__ __forceinline__ double rbx_h2(double rs2, double h) {
+  return __dmul_rn(__dmul_rn(rs2, h), h);
+}
+
+// QuinticSpline.kernel [upstream pysph.base.kernels; SURVEY App. C-3]
+template <int DIM>
+__device__ __forceinline__ double rbx_quintic(double rij, double h) {
+  const double M_1_PI_ = 0.31830988618379067154;
+  double h1 = 1. / h;
+  double q = rij * h1;
+  double fac;
+  if (DIM == 2) fac = (M_1_PI_ * 7.0 / 478.0) * h1 * h1;
+  else if (DIM == 3) fac = (M_1_PI_ / 120.0) * h1 * h1 * h1;
+  else fac = (1.0 / 120.0) * h1;
+  double t3 = 3. - q, t2 = 2. - q, t1 = 1. - q;
+  double val;
+  if (q > 3.0) val = 0.0;
+  else {
+    val = t3 * t3 * t3 * t3 * t3;
+    if (q <= 2.0) val -= 6.0 * t2 * t2 * t2 * t2 * t2;
+    if (q <= 1.0) val += 15. * t1 * t1 * t1 * t1 * t1;
+  }
+  return val * fac;
+}
+
+__device__ __forceinline__ int rbx_cell_coord(double x, double x0, double inv, int n) {
+  int c = (int)floor((x - x0) * inv);
+  return c < 0 ? 0 : (c >= n ? n - 1 : c);
+}
+
+__device__ __forceinline__ double rbx_warp_min(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double rbx_warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double rbx_warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}

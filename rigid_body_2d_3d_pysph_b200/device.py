@@ -1,0 +1,601 @@
+"""Device-resident scene and the host side of the rigid-body step.
+
+``DeviceScene`` owns the HBM layout of one simulation (torch CUDA tensors,
+FP64 / int32 SoA) and drives the C ABI of librbx.so (include/rbx.h).  It is
+what the PySPH-shaped ``Integrator`` replacement calls (SURVEY.md section 8b
+"Callers"); nothing in here does arithmetic of the hot path on the CPU.
+
+HBM layout
+  * global particle order: rigid-body arrays first (in scheme order, each
+    array's particles grouped by body), static boundary arrays after;
+  * per particle (n_total): x y z u v w h m rho (f64), dem_id (i32);
+  * per rigid particle (n_rigid): fx fy fz dx0 dy0 dz0 (f64), body (i32,
+    global body index), is_boundary (i32), normal0/normal (f64 x3);
+  * per body: the reference's own strided constants (xcm[3b+j], R[9b+j], ...)
+    concatenated over arrays, so every ``pa.xcm`` is one contiguous slice;
+  * sparse contact history [ks][n_rigid] (key = source dem_id) x 2 buffers;
+  * the cell list over the source particles
+    (contact_force_is_boundary == 1) with sorted SoA copies.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (RbxCells, RbxDiag, RbxParams, RbxPoints, RbxScene)
+
+CHUNK = 128
+
+_PARTICLE_F64 = ['x', 'y', 'z', 'u', 'v', 'w', 'h', 'm', 'rho']
+_RIGID_F64 = ['fx', 'fy', 'fz', 'dx0', 'dy0', 'dz0']
+# per-body constants: name -> stride
+_BODY_F64 = {'total_mass': 1, 'izz': 1, 'xcm': 3, 'vcm': 3, 'ang_mom': 3,
+             'omega': 3, 'force': 3, 'torque': 3, 'R': 9,
+             'inertia_tensor_inverse_body_frame': 9,
+             'inertia_tensor_inverse_global_frame': 9,
+             'xcm0': 3, 'vcm0': 3, 'ang_mom0': 3, 'R0': 9}
+# names the device overwrites during a step (host copies become stale)
+_MUTATED_PARTICLE = ['x', 'y', 'z', 'u', 'v', 'w', 'fx', 'fy', 'fz', 'normal']
+_MUTATED_BODY = ['xcm', 'vcm', 'ang_mom', 'omega', 'force', 'torque', 'R',
+                 'inertia_tensor_inverse_global_frame', 'xcm0', 'vcm0',
+                 'ang_mom0', 'R0']
+# names whose change invalidates the static tables (source list, h_max, ...)
+_STATIC = ['h', 'm', 'rho', 'dem_id', 'body_id', 'contact_force_is_boundary',
+           'dx0', 'dy0', 'dz0', 'is_boundary', 'normal0', 'total_mass', 'izz',
+           'inertia_tensor_inverse_body_frame', 'eta', 'spacing0']
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+class DeviceScene(object):
+    def __init__(self, arrays, rigid_names, boundary_names=(), dim=3,
+                 kr=1e5, kf=1e3, fric_coeff=0.5, gx=0., gy=0., gz=0.,
+                 planar=False, ks=4, radius_scale=3.0, eta_uniform=None,
+                 cap_cells=None, device=None):
+        if not torch.cuda.is_available():
+            raise _lib.RbxError('DeviceScene needs a CUDA device; the '
+                                'rigid-body path has no CPU fallback')
+        self.lib = _lib.load()
+        self.device = torch.device(device if device is not None else
+                                   'cuda:%d' % torch.cuda.current_device())
+        pas = dict((a.name, a) for a in arrays)
+        self.rigid = [pas[n] for n in rigid_names]
+        self.bounds = [pas[n] for n in boundary_names]
+        self.arrays = self.rigid + self.bounds
+        self.dim = int(dim)
+        self.planar = bool(planar)
+        self.ks = int(ks)
+        self.radius_scale = float(radius_scale)
+        self.kr, self.kf, self.fric_coeff = float(kr), float(kf), \
+            float(fric_coeff)
+        self.g = (float(gx), float(gy), float(gz))
+        self.eta_uniform = eta_uniform
+        self._cap_cells_req = cap_cells
+        self.parity = 0          # history ping-pong
+        self.steps_done = 0
+        self._graph = None
+        self._build_static()
+        for pa in self.arrays:
+            pa.__dict__['_device'] = self
+            pa.__dict__['_host_touched'].clear()
+            pa.__dict__['_device_newer'].clear()
+
+    # ------------------------------------------------------------------
+    def _t(self, arr, dtype):
+        return torch.as_tensor(np.ascontiguousarray(arr), dtype=dtype) \
+            .to(self.device)
+
+    def _build_static(self):
+        dev = self.device
+        f64, i32 = torch.float64, torch.int32
+        # ---- offsets -------------------------------------------------
+        self.p_off, self.b_off = {}, {}
+        off = 0
+        boff = 0
+        for pa in self.rigid:
+            self.p_off[pa.name] = off
+            self.b_off[pa.name] = boff
+            off += pa.get_number_of_particles()
+            boff += int(pa.constants['nb'][0])
+        self.n_rigid = off
+        self.n_bodies = boff
+        for pa in self.bounds:
+            self.p_off[pa.name] = off
+            off += pa.get_number_of_particles()
+        self.n_total = off
+        # ---- particles -----------------------------------------------
+        self.P = {}
+        for n in _PARTICLE_F64:
+            self.P[n] = self._t(np.concatenate(
+                [pa.properties[n] for pa in self.arrays]), f64)
+        self.P['dem_id'] = self._t(np.concatenate(
+            [pa.properties['dem_id'] for pa in self.arrays]), i32)
+        body = []
+        for pa in self.rigid:
+            bid = pa.properties['body_id'].astype(np.int64)
+            dem = pa.properties['dem_id']
+            if bid.size and np.any(np.diff(bid) < 0):
+                raise ValueError(
+                    "array '%s': particles must be grouped by ascending "
+                    'body_id' % pa.name)
+            if bid.size:
+                first = np.searchsorted(bid, np.arange(bid[-1] + 1))
+                first = np.minimum(first, bid.size - 1)
+                if np.any(dem != dem[first[bid]]):
+                    raise ValueError("array '%s': a body carries more than "
+                                     'one dem_id' % pa.name)
+            body.append(bid + self.b_off[pa.name])
+        body = np.concatenate(body) if body else np.zeros(0, np.int64)
+        self.P['body'] = self._t(body, i32)
+        for n in _RIGID_F64:
+            self.P[n] = self._t(np.concatenate(
+                [pa.properties[n] for pa in self.rigid]), f64)
+        have_normals = all('normal' in pa.properties and 'normal0' in
+                           pa.properties and 'is_boundary' in pa.properties
+                           for pa in self.rigid)
+        self.have_normals = have_normals
+        if have_normals:
+            self.P['normal'] = self._t(np.concatenate(
+                [pa.properties['normal'] for pa in self.rigid]), f64)
+            self.P['normal0'] = self._t(np.concatenate(
+                [pa.properties['normal0'] for pa in self.rigid]), f64)
+            self.P['is_boundary'] = self._t(np.concatenate(
+                [pa.properties['is_boundary'] for pa in self.rigid]), i32)
+        # ---- bodies ----------------------------------------------------
+        self.B = {}
+        for n, s in _BODY_F64.items():
+            parts = []
+            for pa in self.rigid:
+                nb = int(pa.constants['nb'][0])
+                if n in pa.constants:
+                    parts.append(np.asarray(pa.constants[n], dtype=np.float64))
+                else:
+                    parts.append(np.zeros(nb * s))
+            self.B[n] = self._t(np.concatenate(parts) if parts
+                                else np.zeros(0), f64)
+        self.B['R_prev'] = self.B['R'].clone()
+        sp = []
+        for pa in self.rigid:
+            nb = int(pa.constants['nb'][0])
+            sp.append(np.full(nb, float(pa.constants['spacing0'][0])))
+        self.B['spacing0'] = self._t(np.concatenate(sp) if sp
+                                     else np.zeros(0), f64)
+        # ---- chunks ----------------------------------------------------
+        counts = np.bincount(body, minlength=self.n_bodies) \
+            if body.size else np.zeros(self.n_bodies, np.int64)
+        bstart = np.concatenate([[0], np.cumsum(counts)])
+        nch = (counts + CHUNK - 1) // CHUNK
+        bc = np.concatenate([[0], np.cumsum(nch)]).astype(np.int64)
+        cb = np.repeat(np.arange(self.n_bodies, dtype=np.int64), nch)
+        within = np.arange(int(bc[-1]), dtype=np.int64) - bc[cb]
+        cs = np.concatenate([bstart[cb] + CHUNK * within, [self.n_rigid]])
+        self.n_chunks = int(bc[-1])
+        self.T = {'chunk_start': self._t(cs, i32),
+                  'chunk_body': self._t(cb, i32),
+                  'body_chunk': self._t(bc, i32),
+                  'chunk_ft': torch.zeros(max(self.n_chunks, 1) * 6,
+                                          dtype=f64, device=dev)}
+        # ---- damping table ---------------------------------------------
+        self.eta_mode = 0
+        self.T['eta'] = None
+        self.T['eta_row'] = None
+        if self.eta_uniform is not None:
+            self.eta_mode = 2
+            self.T['eta'] = self._t(np.array([self.eta_uniform]), f64)
+        else:
+            etas, rows, eo = [], [], 0
+            for pa in self.rigid:
+                nb = int(pa.constants['nb'][0])
+                tnb = int(pa.constants['total_no_bodies'][0])
+                e = np.asarray(pa.constants.get('eta', np.zeros(nb * tnb)),
+                               dtype=np.float64)
+                etas.append(e)
+                rows.append(eo + np.arange(nb, dtype=np.int64) * tnb)
+                eo += e.size
+            eta = np.concatenate(etas) if etas else np.zeros(0)
+            if eta.size and np.any(eta != 0.):
+                self.eta_mode = 1
+                self.T['eta'] = self._t(eta, f64)
+                self.T['eta_row'] = self._t(np.concatenate(rows),
+                                            torch.int64)
+        # ---- sources ---------------------------------------------------
+        cfb = np.concatenate([
+            pa.properties['contact_force_is_boundary']
+            if 'contact_force_is_boundary' in pa.properties
+            else np.zeros(pa.get_number_of_particles())
+            for pa in self.arrays]) if self.arrays else np.zeros(0)
+        src = np.nonzero(cfb == 1.)[0]
+        self.n_src = int(src.size)
+        self.T['src_index'] = self._t(src, i32)
+        h = self.P['h']
+        self.hmax = float(h.max().item()) if h.numel() else 1.0
+        hmin = float(h.min().item()) if h.numel() else 1.0
+        self.h_uniform = self.hmax if hmin == self.hmax else 0.0
+        self.reach = self.radius_scale * self.hmax
+        # ---- history, status, counters ---------------------------------
+        nr = max(self.n_rigid, 1)
+        self.H = []
+        for _ in range(2):
+            self.H.append({
+                'key': torch.full((self.ks * nr,), -1, dtype=i32, device=dev),
+                'dlt': torch.zeros(3 * self.ks * nr, dtype=f64, device=dev),
+                'fn': torch.zeros(3 * self.ks * nr, dtype=f64, device=dev)})
+        self.status = torch.zeros(1, dtype=i32, device=dev)
+        self.counters = torch.zeros(4, dtype=torch.int64, device=dev)
+        # ---- cell list over the sources ----------------------------------
+        self._alloc_cells(max(self.n_src, 1), self.T['src_index'])
+        self._refresh_structs()
+
+    def _alloc_cells(self, cap_points, index):
+        dev = self.device
+        f64, i32 = torch.float64, torch.int32
+        if self._cap_cells_req is not None:
+            cap_cells = int(self._cap_cells_req)
+        else:
+            ncell = 1
+            if index is not None and index.numel():
+                idx = index.long()
+                for n in 'xyz':
+                    v = self.P[n][idx]
+                    ext = float((v.max() - v.min()).item())
+                    ncell *= int(ext / self.reach) + 2
+            # room for the scene to spread by 2x per axis before coarsening
+            cap_cells = int(min(max(8 * ncell, 4096), 1 << 26))
+        self.cap_cells = cap_cells
+        self.C = {'info': torch.zeros(64, dtype=torch.uint8, device=dev),
+                  'cell_start': torch.zeros(cap_cells + 1, dtype=i32,
+                                            device=dev),
+                  'cell_of': torch.zeros(cap_points, dtype=i32, device=dev),
+                  'rank': torch.zeros(cap_points, dtype=i32, device=dev),
+                  'gidx': torch.zeros(cap_points, dtype=i32, device=dev),
+                  'sdem': torch.zeros(cap_points, dtype=i32, device=dev)}
+        for n in ('sx', 'sy', 'sz', 'sh'):
+            self.C[n] = torch.zeros(cap_points, dtype=f64, device=dev)
+        self.cap_points = cap_points
+        nbytes = self.lib.rbx_cells_workspace_bytes(cap_cells, cap_points)
+        self.workspace = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+
+    # ------------------------------------------------------------------
+    def _refresh_structs(self):
+        P, B, T = self.P, self.B, self.T
+        s = RbxScene()
+        s.n_total, s.n_rigid, s.n_bodies = self.n_total, self.n_rigid, \
+            self.n_bodies
+        s.n_chunks, s.dim, s.ks = self.n_chunks, self.dim, self.ks
+        s.eta_mode, s.planar = self.eta_mode, int(self.planar)
+        for n in ['x', 'y', 'z', 'u', 'v', 'w', 'h', 'm', 'rho', 'dem_id',
+                  'fx', 'fy', 'fz', 'dx0', 'dy0', 'dz0', 'body']:
+            setattr(s, n, _ptr(P[n]))
+        if self.have_normals:
+            s.is_boundary = _ptr(P['is_boundary'])
+            s.normal0 = _ptr(P['normal0'])
+            s.normal = _ptr(P['normal'])
+        for n in ['chunk_start', 'chunk_body', 'body_chunk', 'chunk_ft',
+                  'eta', 'eta_row']:
+            setattr(s, n, _ptr(T[n]))
+        for n in ['total_mass', 'izz', 'spacing0', 'xcm', 'vcm', 'ang_mom',
+                  'omega', 'force', 'torque', 'R', 'R_prev', 'xcm0', 'vcm0',
+                  'ang_mom0', 'R0']:
+            setattr(s, n, _ptr(B[n]))
+        s.iinv_b = _ptr(B['inertia_tensor_inverse_body_frame'])
+        s.iinv_g = _ptr(B['inertia_tensor_inverse_global_frame'])
+        s.status = _ptr(self.status)
+        s.counters = _ptr(self.counters)
+        self._scene = [None, None]
+        for par in (0, 1):
+            c = RbxScene.from_buffer_copy(s)
+            hin, hout = self.H[par], self.H[1 - par]
+            c.hist_key_in, c.hist_dlt_in, c.hist_fn_in = \
+                _ptr(hin['key']), _ptr(hin['dlt']), _ptr(hin['fn'])
+            c.hist_key_out, c.hist_dlt_out, c.hist_fn_out = \
+                _ptr(hout['key']), _ptr(hout['dlt']), _ptr(hout['fn'])
+            self._scene[par] = c
+        self._src = self.points(self.T['src_index'])
+        c = RbxCells()
+        c.cap_cells, c.cap_points = self.cap_cells, self.cap_points
+        for n in ['info', 'cell_start', 'cell_of', 'rank', 'gidx', 'sx', 'sy',
+                  'sz', 'sh', 'sdem']:
+            setattr(c, n, _ptr(self.C[n]))
+        self._cells = c
+        self._graph = None
+
+    def points(self, index=None, n=None):
+        p = RbxPoints()
+        if index is not None:
+            p.n = int(index.numel())
+            p.index = _ptr(index)
+        else:
+            p.n = int(self.n_total if n is None else n)
+            p.index = None
+        p.x, p.y, p.z, p.h = (_ptr(self.P[k]) for k in 'xyzh')
+        p.dem_id = _ptr(self.P['dem_id'])
+        return p
+
+    def params(self, dt):
+        return RbxParams(self.radius_scale, self.kr, self.kf,
+                         self.fric_coeff, self.g[0], self.g[1], self.g[2],
+                         float(dt), self.reach, self.h_uniform)
+
+    @property
+    def stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    @property
+    def scene(self):
+        return self._scene[self.parity]
+
+    # ------------------------------------------------------------------
+    # host <-> device coherence
+    # ------------------------------------------------------------------
+    def _slice(self, pa, name):
+        """Device tensor slice that mirrors pa.<name>, or None."""
+        if name in _PARTICLE_F64 or name == 'dem_id':
+            o = self.p_off[pa.name]
+            return self.P[name][o:o + pa.get_number_of_particles()]
+        if pa in self.rigid:
+            o = self.p_off[pa.name]
+            n = pa.get_number_of_particles()
+            if name in _RIGID_F64 or (name == 'is_boundary' and
+                                      self.have_normals):
+                return self.P[name][o:o + n]
+            if name in ('normal', 'normal0') and self.have_normals:
+                return self.P[name][3 * o:3 * (o + n)]
+            if name in _BODY_F64:
+                s = _BODY_F64[name]
+                bo = self.b_off[pa.name]
+                nb = int(pa.constants['nb'][0])
+                return self.B[name][s * bo:s * (bo + nb)]
+        return None
+
+    def pull(self, pa, name):
+        t = self._slice(pa, name)
+        if t is None:
+            return
+        host = pa.properties[name] if name in pa.properties else \
+            pa.constants[name]
+        host[:] = t.cpu().numpy()
+
+    def push_touched(self):
+        """Upload whatever the host code touched since the last step."""
+        rebuild = False
+        for pa in self.arrays:
+            touched = pa.__dict__['_host_touched']
+            if not touched:
+                continue
+            if touched & set(_STATIC):
+                rebuild = True
+            for name in list(touched):
+                t = self._slice(pa, name)
+                if t is None:
+                    continue
+                host = pa.properties[name] if name in pa.properties else \
+                    pa.constants[name]
+                t.copy_(torch.as_tensor(host, dtype=t.dtype))
+            touched.clear()
+        if rebuild:
+            for pa in self.arrays:
+                for n in list(pa.__dict__['_device_newer']):
+                    self.pull(pa, n)
+                pa.__dict__['_device_newer'].clear()
+            hist, parity = self.H, self.parity
+            self._build_static()
+            self.H, self.parity = hist, parity
+            self._refresh_structs()
+
+    def mark_device_newer(self):
+        for pa in self.rigid:
+            dn = pa.__dict__['_device_newer']
+            for n in _MUTATED_PARTICLE:
+                if n in pa.properties:
+                    dn.add(n)
+            for n in _MUTATED_BODY:
+                if n in pa.constants:
+                    dn.add(n)
+
+    def sync_to_host(self):
+        """Bring every stale host array up to date (before output dumps)."""
+        for pa in self.arrays:
+            for n in list(pa.__dict__['_device_newer']):
+                self.pull(pa, n)
+            pa.__dict__['_device_newer'].clear()
+
+    # ------------------------------------------------------------------
+    # operations (thin wrappers over the C ABI)
+    # ------------------------------------------------------------------
+    def cells_build(self, points=None, cells=None):
+        pts = points if points is not None else self._src
+        c = cells if cells is not None else self._cells
+        _lib.check(self.lib.rbx_cells_build(
+            ctypes.byref(pts), ctypes.byref(c), self.reach,
+            _ptr(self.status), _ptr(self.workspace), self.workspace.numel(),
+            self.stream), 'rbx_cells_build')
+
+    def contact(self, dt, diag=None):
+        p = self.params(dt)
+        _lib.check(self.lib.rbx_contact_mofidi(
+            ctypes.byref(self.scene), ctypes.byref(self._cells),
+            ctypes.byref(p), ctypes.byref(diag) if diag is not None else None,
+            self.stream), 'rbx_contact_mofidi')
+        self.parity ^= 1
+
+    def reduce_bodies(self):
+        _lib.check(self.lib.rbx_reduce_bodies(ctypes.byref(self.scene),
+                                              self.stream), 'reduce')
+
+    def gtvf_kick(self, dt):
+        _lib.check(self.lib.rbx_gtvf_kick(ctypes.byref(self.scene), float(dt),
+                                          self.stream), 'kick')
+
+    def gtvf_drift(self, dt):
+        _lib.check(self.lib.rbx_gtvf_drift(ctypes.byref(self.scene),
+                                           float(dt), self.stream), 'drift')
+
+    def pose(self, flags):
+        _lib.check(self.lib.rbx_pose_particles(ctypes.byref(self.scene),
+                                               int(flags), self.stream),
+                   'pose')
+
+    def rk2_stage(self, stage, dt, fix_q7=False):
+        _lib.check(self.lib.rbx_rk2_stage(ctypes.byref(self.scene),
+                                          int(stage), float(dt), int(fix_q7),
+                                          self.stream), 'rk2')
+
+    def _gtvf_step_call(self, p, flags=0):
+        _lib.check(self.lib.rbx_gtvf_step(
+            ctypes.byref(self.scene), ctypes.byref(self._src),
+            ctypes.byref(self._cells), ctypes.byref(p), _ptr(self.workspace),
+            self.workspace.numel(), int(flags), self.stream), 'rbx_gtvf_step')
+        self.parity ^= 1
+
+    def gtvf_step(self, dt, nsteps=1, graph=False):
+        """nsteps x GTVFIntegrator.one_timestep on the device."""
+        self.push_touched()
+        p = self.params(dt)
+        if graph and nsteps >= 4:
+            self._run_graph(p, nsteps)
+        else:
+            for _ in range(nsteps):
+                self._gtvf_step_call(p)
+        self.steps_done += nsteps
+        self.mark_device_newer()
+
+    def _run_graph(self, p, nsteps):
+        """Two steps (one history ping-pong period) captured as a CUDA graph:
+        small scenes are launch-bound (about a dozen launches per step)."""
+        key = (p.dt, self.parity)
+        if self._graph is None or self._graph[0] != key:
+            start = self.parity
+            g = torch.cuda.CUDAGraph()
+            s = torch.cuda.Stream(self.device)
+            s.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(s):
+                self._gtvf_step_call(p)     # warm-up outside capture
+                self._gtvf_step_call(p)
+                s.synchronize()
+                with torch.cuda.graph(g, stream=s):
+                    self._gtvf_step_call(p)
+                    self._gtvf_step_call(p)
+            torch.cuda.current_stream(self.device).wait_stream(s)
+            assert self.parity == start
+            self._graph = (key, g)
+            nsteps -= 2
+        g = self._graph[1]
+        while nsteps >= 2:
+            g.replay()
+            nsteps -= 2
+        for _ in range(nsteps):
+            self._gtvf_step_call(p)
+
+    def rk2_step(self, dt, nsteps=1, fix_q7=False):
+        """EPEC sequencing with the RK2 stepper."""
+        self.push_touched()
+        for _ in range(nsteps):
+            self.rk2_stage(0, dt, fix_q7)
+            self.cells_build()
+            self.contact(dt)
+            self.reduce_bodies()
+            self.rk2_stage(1, dt, fix_q7)
+            self.pose(_lib.POSE_POS | _lib.POSE_VEL)
+            self.cells_build()
+            self.contact(dt)
+            self.reduce_bodies()
+            self.rk2_stage(2, dt, fix_q7)
+            self.pose(_lib.POSE_POS | _lib.POSE_VEL)
+        self.steps_done += nsteps
+        self.mark_device_newer()
+
+    # ------------------------------------------------------------------
+    def check_status(self, raise_on_error=True):
+        st = int(self.status.item()) & 0xffffffff
+        msgs = []
+        if st & _lib.STATUS_SLOT_OVERFLOW:
+            msgs.append('a particle touches more than %d bodies' %
+                        _lib.RBX_MAX_KEYS)
+        if st & _lib.STATUS_HIST_OVERFLOW:
+            msgs.append('more than ks=%d simultaneous contacts on a particle'
+                        % self.ks)
+        if st & _lib.STATUS_LIST_OVERFLOW:
+            msgs.append('per-particle neighbour list overflow')
+        if msgs and raise_on_error:
+            raise _lib.RbxError('device status 0x%x: %s' %
+                                (st, '; '.join(msgs)))
+        return st
+
+    def read_counters(self, reset=False):
+        c = self.counters.cpu().numpy().copy()
+        if reset:
+            self.counters.zero_()
+        return {'gated_pairs': int(c[0]), 'active_slots': int(c[1]),
+                'candidates': int(c[2])}
+
+    def grid_info(self):
+        raw = self.C['info'].cpu().numpy().tobytes()
+        return _lib.RbxGridInfo.from_buffer_copy(raw)
+
+    # ------------------------------------------------------------------
+    # parity helpers
+    # ------------------------------------------------------------------
+    def make_diag(self):
+        nr = max(self.n_rigid, 1)
+        K = _lib.RBX_MAX_KEYS
+        dev = self.device
+        t = {'key': torch.full((K * nr,), -1, dtype=torch.int32, device=dev),
+             'closest': torch.full((K * nr,), -1, dtype=torch.int32,
+                                   device=dev)}
+        for n in ['nx', 'ny', 'nz', 'dist', 'overlap', 'ftx', 'fty', 'ftz']:
+            t[n] = torch.zeros(K * nr, dtype=torch.float64, device=dev)
+        d = RbxDiag()
+        for n, v in t.items():
+            setattr(d, n, _ptr(v))
+        return d, t
+
+    def history(self):
+        """Current history as host arrays: key [ks,n], dlt/fn [3,ks,n]."""
+        h = self.H[self.parity]
+        nr = max(self.n_rigid, 1)
+        return (h['key'].view(self.ks, nr).cpu().numpy(),
+                h['dlt'].view(3, self.ks, nr).cpu().numpy(),
+                h['fn'].view(3, self.ks, nr).cpu().numpy())
+
+    def pairs(self, dst_name, src_name):
+        """NNPS neighbour pairs (i, j) of array dst among array src, as a
+        sorted int array [npairs, 2] of array-local indices (parity mode)."""
+        pas = dict((a.name, a) for a in self.arrays)
+        dev = self.device
+        so, sn = self.p_off[src_name], pas[src_name].get_number_of_particles()
+        do, dn = self.p_off[dst_name], pas[dst_name].get_number_of_particles()
+        sidx = torch.arange(so, so + sn, dtype=torch.int32, device=dev)
+        didx = torch.arange(do, do + dn, dtype=torch.int32, device=dev)
+        saved = (self.C, self.cap_cells, self.cap_points, self.workspace,
+                 self._cells)
+        self._alloc_cells(max(sn, 1), sidx)
+        c = RbxCells()
+        c.cap_cells, c.cap_points = self.cap_cells, self.cap_points
+        for n in ['info', 'cell_start', 'cell_of', 'rank', 'gidx', 'sx', 'sy',
+                  'sz', 'sh', 'sdem']:
+            setattr(c, n, _ptr(self.C[n]))
+        self.cells_build(self.points(sidx), c)
+        dpts = self.points(didx)
+        counts = torch.zeros(max(dn, 1), dtype=torch.int32, device=dev)
+        _lib.check(self.lib.rbx_pairs_dump(
+            ctypes.byref(dpts), ctypes.byref(c), self.radius_scale,
+            _ptr(counts), None, None, self.stream), 'pairs count')
+        offs = torch.zeros(dn + 1, dtype=torch.int64, device=dev)
+        offs[1:] = torch.cumsum(counts[:dn].long(), 0)
+        tot = int(offs[-1].item())
+        idx = torch.zeros(max(tot, 1), dtype=torch.int32, device=dev)
+        _lib.check(self.lib.rbx_pairs_dump(
+            ctypes.byref(dpts), ctypes.byref(c), self.radius_scale,
+            _ptr(counts), _ptr(offs), _ptr(idx), self.stream), 'pairs dump')
+        torch.cuda.synchronize(dev)
+        (self.C, self.cap_cells, self.cap_points, self.workspace,
+         self._cells) = saved
+        i = torch.repeat_interleave(torch.arange(dn, device=dev),
+                                    counts[:dn].long())
+        j = idx[:tot].long() - so
+        out = torch.stack([i, j], 1).cpu().numpy().astype(np.int32)
+        order = np.lexsort((out[:, 1], out[:, 0]))
+        return out[order]

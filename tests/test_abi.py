@@ -1,0 +1,44 @@
+"""The C-ABI library loads and exports every symbol include/rbx.h declares
+(no compute calls: this test runs without a GPU)."""
+import ctypes
+import os
+import re
+
+from rigid_body_2d_3d_pysph_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ensure_built():
+    from rigid_body_2d_3d_pysph_b200.csrc import build
+    build.build()
+
+
+def test_header_symbols_exported():
+    _ensure_built()
+    hdr = open(os.path.join(ROOT, 'include', 'rbx.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    declared = set(re.findall(r'\b(rbx_[a-z0-9_]+)\s*\(', hdr))
+    assert declared, 'no declarations found'
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for sym in sorted(declared):
+        assert hasattr(L, sym), 'missing symbol %s' % sym
+    assert declared == set(_lib.SYMBOLS)
+
+
+def test_struct_mirrors_match_library():
+    _ensure_built()
+    L = _lib.load()      # raises on any sizeof mismatch
+    assert L.rbx_version() == 100
+    assert L.rbx_strerror(-2) == b'workspace too small'
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, '_lib', None)
+    monkeypatch.setattr(_lib, 'LIB_PATH', str(tmp_path / 'nope.so'))
+    try:
+        _lib.load()
+    except _lib.RbxError as e:
+        assert 'no CPU fallback' in str(e)
+    else:
+        raise AssertionError('load() must raise when librbx.so is missing')

@@ -1,0 +1,181 @@
+"""CUDA path (through the C ABI) against the golden fixtures and the oracle.
+
+Tolerances (BASELINE.json north_star): neighbour pairs bit-exact as sorted
+index pairs; particle forces and per-body force/torque 1e-10 relative in FP64
+(cancelling sums scaled by the sum of |terms|); trajectories 1e-6 relative
+over the stated horizon (here the fixtures' 3-120 steps, where 1e-9 holds).
+"""
+import numpy as np
+import pytest
+
+from tests.util import CASES, assert_close, load_case
+
+pytestmark = pytest.mark.gpu
+
+FORCE_RTOL = 1e-10
+TRAJ_RTOL = 1e-9
+
+
+def _scene(arrays, meta, **kw):
+    from rigid_body_2d_3d_pysph_b200.device import DeviceScene
+    return DeviceScene(arrays, meta['rigid'], meta['boundaries'],
+                       dim=meta['dim'], kr=meta['kr'], kf=meta['kf'],
+                       fric_coeff=meta['fric_coeff'], gx=meta['gx'],
+                       gy=meta['gy'], gz=meta['gz'],
+                       planar=(meta['stepper'] == 'gtvf2d'), **kw)
+
+
+def _get(pa, n):
+    return getattr(pa, n)
+
+
+def _compare_state(name, step, arrays, ref, rigid):
+    for pa in arrays:
+        if pa.name not in rigid:
+            continue
+        pre = 'ref/%d/%s/' % (step, pa.name)
+        f = np.sqrt(ref[pre + 'fx']**2 + ref[pre + 'fy']**2 +
+                    ref[pre + 'fz']**2)
+        fscale = max(f.sum(), 1e-300)
+        for n in ('fx', 'fy', 'fz', 'force'):
+            assert_close(_get(pa, n), ref[pre + n], FORCE_RTOL,
+                         '%s step %d %s.%s' % (name, step, pa.name, n),
+                         fscale)
+        lever = max(np.abs(ref[pre + 'x'] - ref[pre + 'xcm'][0]).max(),
+                    np.abs(ref[pre + 'y'] - ref[pre + 'xcm'][1]).max(), 1e-300)
+        assert_close(_get(pa, 'torque'), ref[pre + 'torque'], FORCE_RTOL,
+                     '%s step %d torque' % (name, step), fscale * lever)
+        for n in ('x', 'y', 'z', 'u', 'v', 'w', 'xcm', 'vcm', 'omega',
+                  'ang_mom', 'R'):
+            want = ref[pre + n]
+            scale = max(np.abs(want).max(), 1e-3)
+            assert_close(_get(pa, n), want, TRAJ_RTOL,
+                         '%s step %d %s.%s' % (name, step, pa.name, n), scale)
+
+
+@pytest.mark.parametrize('name', [c for c in CASES if c != 'rk2_3d'])
+def test_gtvf_fused_step_matches_reference(name):
+    arrays, ref, meta = load_case(name)
+    sc = _scene(arrays, meta)
+    done = 0
+    for step in meta['save_steps']:
+        if step > meta['nsteps']:
+            break
+        sc.gtvf_step(meta['dt'], step - done)
+        done = step
+        sc.check_status()
+        _compare_state(name, step, arrays, ref, meta['rigid'])
+
+
+@pytest.mark.parametrize('name', ['wall2d', 'collide2d', 'cubes3d',
+                                  'wall2d_normal', 'wall2d_rest'])
+def test_unfused_ops_and_slots_match_reference(name):
+    """Same step through the individual entry points, plus every dense slot
+    array of the reference rebuilt from the sparse slots."""
+    from rigid_body_2d_3d_pysph_b200 import _lib
+    arrays, ref, meta = load_case(name)
+    sc = _scene(arrays, meta)
+    dt = meta['dt']
+    diag, dt_t = sc.make_diag()
+    K = _lib.RBX_MAX_KEYS
+    for step in range(1, meta['nsteps'] + 1):
+        sc.push_touched()
+        sc.gtvf_kick(dt)
+        sc.pose(_lib.POSE_VEL)
+        sc.gtvf_drift(dt)
+        sc.pose(_lib.POSE_POS | _lib.POSE_NORMALS)
+        sc.cells_build()
+        sc.contact(dt, diag)
+        sc.reduce_bodies()
+        sc.gtvf_kick(dt)
+        sc.pose(_lib.POSE_VEL)
+        sc.mark_device_newer()
+        if step not in meta['save_steps']:
+            continue
+        sc.check_status()
+        _compare_state(name, step, arrays, ref, meta['rigid'])
+        hkey, hdlt, hfn = sc.history()
+        dkey = dt_t['key'].view(K, -1).cpu().numpy()
+        for pa in sc.rigid:
+            o = sc.p_off[pa.name]
+            n = pa.get_number_of_particles()
+            tnb = int(pa.total_no_bodies[0])
+            pre = 'ref/%d/%s/' % (step, pa.name)
+            dense = dict((k, np.zeros(n * tnb)) for k in
+                         ['contact_force_normal_x', 'contact_force_normal_y',
+                          'contact_force_normal_z', 'contact_force_dist',
+                          'overlap', 'ft_x', 'ft_y', 'ft_z', 'fn_x', 'fn_y',
+                          'fn_z', 'delta_lt_x', 'delta_lt_y', 'delta_lt_z'])
+            dmap = {'contact_force_normal_x': 'nx',
+                    'contact_force_normal_y': 'ny',
+                    'contact_force_normal_z': 'nz',
+                    'contact_force_dist': 'dist', 'overlap': 'overlap',
+                    'ft_x': 'ftx', 'ft_y': 'fty', 'ft_z': 'ftz'}
+            ii = np.arange(n)
+            for k in range(K):
+                key = dkey[k, o:o + n]
+                m = key >= 0
+                t2 = tnb * ii[m] + key[m]
+                for dn, sn in dmap.items():
+                    v = dt_t[sn].view(K, -1)[k, o:o + n].cpu().numpy()
+                    dense[dn][t2] = v[m]
+            for s in range(sc.ks):
+                key = hkey[s, o:o + n]
+                m = key >= 0
+                t2 = tnb * ii[m] + key[m]
+                for c, ax in enumerate('xyz'):
+                    dense['delta_lt_' + ax][t2] = hdlt[c, s, o:o + n][m]
+                    dense['fn_' + ax][t2] = hfn[c, s, o:o + n][m]
+            fsc = max(np.abs(ref[pre + 'fn_x']).max(),
+                      np.abs(ref[pre + 'fn_y']).max(),
+                      np.abs(ref[pre + 'fn_z']).max(), 1e-300)
+            for dn, got in dense.items():
+                want = ref[pre + dn]
+                scale = fsc if dn[:2] in ('fn', 'ft') else \
+                    max(np.abs(want[~np.isnan(want)]).max(), 1e-300) \
+                    if (~np.isnan(want)).any() else 1.0
+                assert_close(got, want, 1e-9, '%s step %d %s' %
+                             (name, step, dn), scale)
+
+
+def test_rk2_matches_reference():
+    arrays, ref, meta = load_case('rk2_3d')
+    sc = _scene(arrays, meta)
+    done = 0
+    for step in meta['save_steps']:
+        sc.rk2_step(meta['dt'], step - done)
+        done = step
+        sc.check_status()
+        _compare_state('rk2_3d', step, arrays, ref, meta['rigid'])
+
+
+@pytest.mark.parametrize('name', ['cubes3d', 'collide2d', 'wall2d'])
+def test_pair_sets_bit_exact(name):
+    """Neighbour pairs of the CUDA cell list == oracle NNPS, as sorted pairs."""
+    from oracle import rbo
+    arrays, ref, meta = load_case(name)
+    sc = _scene(arrays, meta)
+    names = [a.name for a in arrays]
+    for d in meta['rigid']:
+        for s in names:
+            off, idx = rbo.nnps_pairs(arrays, names.index(d), names.index(s))
+            want = np.stack([np.repeat(np.arange(len(off) - 1),
+                                       np.diff(off)), idx], 1).astype(np.int32)
+            got = sc.pairs(d, s)
+            assert np.array_equal(got, want), (name, d, s, got.shape,
+                                               want.shape)
+
+
+def test_graph_replay_equals_eager():
+    arrays, ref, meta = load_case('cubes3d')
+    arrays2, _, _ = load_case('cubes3d')
+    a = _scene(arrays, meta)
+    b = _scene(arrays2, meta)
+    a.gtvf_step(meta['dt'], 40)
+    b.gtvf_step(meta['dt'], 40, graph=True)
+    a.check_status()
+    b.check_status()
+    for pa, pb in zip(arrays, arrays2):
+        if pa.name in meta['rigid']:
+            for n in ('x', 'y', 'z', 'fx', 'fy', 'fz', 'xcm', 'R'):
+                assert np.array_equal(getattr(pa, n), getattr(pb, n)), n
