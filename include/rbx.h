@@ -42,13 +42,13 @@ typedef enum {
 } RbxError;
 
 /* bits of the device status word */
-#define RBX_STATUS_SLOT_OVERFLOW 1u  /* > RBX_MAX_KEYS bodies touch a particle */
+#define RBX_STATUS_SLOT_OVERFLOW 1u  /* diagnostics only: > RBX_MAX_KEYS slots */
 #define RBX_STATUS_HIST_OVERFLOW 2u  /* > ks simultaneous contacts            */
 #define RBX_STATUS_LIST_OVERFLOW 4u  /* per-particle neighbour list full       */
 #define RBX_STATUS_GRID_COARSENED 8u /* cell size enlarged to fit cap_cells    */
 #define RBX_STATUS_LVC_OVERFLOW 16u  /* LVC tangential history `limit` hit     */
 
-#define RBX_MAX_KEYS 8   /* distinct source bodies per particle per step */
+#define RBX_MAX_KEYS 8   /* slots per particle the optional RbxDiag arrays hold */
 
 /* Uniform grid description, written on the device by rbx_cells_build. */
 typedef struct {

@@ -67,12 +67,13 @@ class RboParams(ctypes.Structure):
                 ('kr', ctypes.c_double), ('kf', ctypes.c_double),
                 ('fric_coeff', ctypes.c_double), ('gx', ctypes.c_double),
                 ('gy', ctypes.c_double), ('gz', ctypes.c_double),
-                ('dt', ctypes.c_double)]
+                ('dt', ctypes.c_double), ('eta_uniform', ctypes.c_double)]
 
 
 def make_params(dim, dt, kr=1e5, kf=1e3, fric_coeff=0.5, gx=0., gy=0., gz=0.,
-                radius_scale=3.0):
-    return RboParams(dim, radius_scale, kr, kf, fric_coeff, gx, gy, gz, dt)
+                radius_scale=3.0, eta_uniform=-1.0):
+    return RboParams(dim, radius_scale, kr, kf, fric_coeff, gx, gy, gz, dt,
+                     eta_uniform)
 
 
 def _get(pa, name):

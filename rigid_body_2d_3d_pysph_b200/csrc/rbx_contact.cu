@@ -37,14 +37,19 @@ struct SlotAcc {
   int gmin;               // its global index (tie rule: lowest index)
 };
 
+constexpr int kWarps = RBX_CHUNK / 32;
+constexpr int kBatch = 4;   // staged candidates per thread per iteration
+
 template <int DIM, bool UNIFORM_H>
-__global__ void __launch_bounds__(RBX_CHUNK)
+__global__ void __launch_bounds__(RBX_CHUNK, 4)
 k_contact(RbxScene S, RbxCells C, RbxParams P, RbxDiag D, double reach, double h_uniform) {
   __shared__ double t_x[RBX_TILE], t_y[RBX_TILE], t_z[RBX_TILE];
   __shared__ double t_h[UNIFORM_H ? 1 : RBX_TILE];
   __shared__ int t_pos[RBX_TILE], t_dem[RBX_TILE];
-  __shared__ double red[RBX_CHUNK / 32][6];
-  __shared__ int wtot[2][RBX_CHUNK / 32];
+  __shared__ double red[kWarps][6];
+  __shared__ int wtot[2][kBatch][kWarps];
+  __shared__ int row_s[RBX_CHUNK], row_off[RBX_CHUNK + 1];
+  __shared__ int wscan[kWarps];
   __shared__ int range[6];
   __shared__ unsigned long long cnt_s[3];
 
@@ -79,7 +84,7 @@ k_contact(RbxScene S, RbxCells C, RbxParams P, RbxDiag D, double reach, double h
   for (int a = 0; a < 3; a++) {
     blo[a] = red[0][a]; bhi[a] = red[0][3 + a];
 #pragma unroll
-    for (int w2 = 1; w2 < RBX_CHUNK / 32; w2++) {
+    for (int w2 = 1; w2 < kWarps; w2++) {
       blo[a] = fmin(blo[a], red[w2][a]);
       bhi[a] = fmax(bhi[a], red[w2][3 + a]);
     }
@@ -97,6 +102,8 @@ k_contact(RbxScene S, RbxCells C, RbxParams P, RbxDiag D, double reach, double h
   __syncthreads();
   const int cx0 = range[0], cx1 = range[1], cy0 = range[2], cy1 = range[3];
   const int cz0 = range[4], cz1 = range[5];
+  const int nry = cy1 - cy0 + 1;
+  const int nrows = nry * (cz1 - cz0 + 1);
 
   // ---- per-thread neighbour list (local memory, L1 resident) -------------
   int l_pos[RBX_LISTCAP];
@@ -117,9 +124,11 @@ k_contact(RbxScene S, RbxCells C, RbxParams P, RbxDiag D, double reach, double h
     if (valid) {
       ncand += (unsigned long long)tile_cnt;
       for (int j = 0; j < tile_cnt; j++) {
-        double r2 = rbx_r2(px - t_x[j], py - t_y[j], pz - t_z[j]);
-        double hj2 = UNIFORM_H ? hj2_u : rbx_h2(rs2, t_h[j]);
-        if (r2 < hi2 || r2 < hj2) {
+        const double r2 = rbx_r2(px - t_x[j], py - t_y[j], pz - t_z[j]);
+        bool hit = r2 < hi2;
+        if (!UNIFORM_H) hit = hit || (r2 < rbx_h2(rs2, t_h[j]));
+        else hit = hit || (r2 < hj2_u);
+        if (hit) {
           if (nlist < RBX_LISTCAP) {
             l_pos[nlist] = t_pos[j];
             l_dem[nlist] = t_dem[j];
@@ -134,49 +143,103 @@ k_contact(RbxScene S, RbxCells C, RbxParams P, RbxDiag D, double reach, double h
     tile_cnt = 0;
   };
 
-  // ---- 2./3. stage rows, flush tiles --------------------------------------
-  for (int cz = cz0; cz <= cz1; cz++) {
-    for (int cy = cy0; cy <= cy1; cy++) {
+  // ---- 2./3. stage the cell rows overlapping the box ----------------------
+  // Rows (cy, cz) are contiguous index ranges of the sorted arrays.  All row
+  // bounds are fetched at once (one row per thread), prefix-summed into one
+  // flat candidate sequence, and that sequence is streamed kBatch*128
+  // entries per iteration so that every thread has kBatch independent loads
+  // in flight per barrier.
+  for (int rb = 0; rb < nrows; rb += RBX_CHUNK) {
+    const int r = rb + tid;
+    int s0 = 0, len = 0;
+    if (r < nrows) {
+      const int cy = cy0 + r % nry, cz = cz0 + r / nry;
       const int row = (cz * gi.ny + cy) * gi.nx;
-      const int rs = C.cell_start[row + cx0], re = C.cell_start[row + cx1 + 1];
-      for (int base = rs; base < re; base += RBX_CHUNK) {
-        if (tile_cnt + RBX_CHUNK > RBX_TILE) phase_a();
-        const int q = base + tid;
-        bool keep = false;
-        double sx = 0, sy = 0, sz = 0, sh = 0;
-        int sd = 0;
-        if (q < re) {
-          sd = C.sdem[q];
-          sx = C.sx[q]; sy = C.sy[q]; sz = C.sz[q];
-          if (!UNIFORM_H) sh = C.sh[q];
-          keep = (sd != my_dem) && sx >= blo[0] && sx <= bhi[0] && sy >= blo[1] &&
-                 sy <= bhi[1] && sz >= blo[2] && sz <= bhi[2];
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        const int buf = it & 1;
-        if (lane == 0) wtot[buf][wid] = __popc(bal);
-        __syncthreads();
-        int off = tile_cnt, tot = 0;
+      s0 = C.cell_start[row + cx0];
+      len = C.cell_start[row + cx1 + 1] - s0;
+    }
+    int inc = len;
 #pragma unroll
-        for (int w2 = 0; w2 < RBX_CHUNK / 32; w2++) {
-          int c = wtot[buf][w2];
-          if (w2 < wid) off += c;
-          tot += c;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    __syncthreads();            // previous users of row_* / wscan are done
+    if (lane == 31) wscan[wid] = inc;
+    __syncthreads();
+    int woff = 0;
+#pragma unroll
+    for (int w2 = 0; w2 < kWarps; w2++) if (w2 < wid) woff += wscan[w2];
+    row_s[tid] = s0;
+    row_off[tid] = woff + inc - len;
+    if (tid == RBX_CHUNK - 1) row_off[RBX_CHUNK] = woff + inc;
+    __syncthreads();
+    const int total = row_off[RBX_CHUNK];
+
+    for (int base = 0; base < total; base += kBatch * RBX_CHUNK) {
+      if (tile_cnt + kBatch * RBX_CHUNK > RBX_TILE) phase_a();
+      bool keep[kBatch];
+      double sx[kBatch], sy[kBatch], sz[kBatch], sh[kBatch];
+      int sd[kBatch], sq[kBatch];
+#pragma unroll
+      for (int k = 0; k < kBatch; k++) {
+        const int f = base + k * RBX_CHUNK + tid;
+        keep[k] = false;
+        sq[k] = -1;
+        if (f < total) {
+          // largest r with row_off[r] <= f  (row_off is non-decreasing)
+          int lo = 0, hi = RBX_CHUNK - 1;
+#pragma unroll
+          for (int stp = 0; stp < 7; stp++) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (row_off[mid] <= f) lo = mid; else hi = mid - 1;
+          }
+          sq[k] = row_s[lo] + (f - row_off[lo]);
         }
-        if (keep) {
-          const int dst = off + __popc(bal & ((1u << lane) - 1u));
-          t_x[dst] = sx; t_y[dst] = sy; t_z[dst] = sz;
-          if (!UNIFORM_H) t_h[dst] = sh;
-          t_pos[dst] = q; t_dem[dst] = sd;
-        }
-        tile_cnt += tot;
-        it++;
       }
+#pragma unroll
+      for (int k = 0; k < kBatch; k++) {
+        if (sq[k] >= 0) {
+          sd[k] = C.sdem[sq[k]];
+          sx[k] = C.sx[sq[k]]; sy[k] = C.sy[sq[k]]; sz[k] = C.sz[sq[k]];
+          if (!UNIFORM_H) sh[k] = C.sh[sq[k]];
+        }
+      }
+      const int buf = it & 1;
+      unsigned bal[kBatch];
+#pragma unroll
+      for (int k = 0; k < kBatch; k++) {
+        if (sq[k] >= 0)
+          keep[k] = (sd[k] != my_dem) && sx[k] >= blo[0] && sx[k] <= bhi[0] &&
+                    sy[k] >= blo[1] && sy[k] <= bhi[1] && sz[k] >= blo[2] && sz[k] <= bhi[2];
+        bal[k] = __ballot_sync(0xffffffffu, keep[k]);
+        if (lane == 0) wtot[buf][k][wid] = __popc(bal[k]);
+      }
+      __syncthreads();
+      int run = tile_cnt;
+#pragma unroll
+      for (int k = 0; k < kBatch; k++) {
+        int off = run;
+#pragma unroll
+        for (int w2 = 0; w2 < kWarps; w2++) {
+          const int c = wtot[buf][k][w2];
+          if (w2 < wid) off += c;
+          run += c;
+        }
+        if (keep[k]) {
+          const int dst = off + __popc(bal[k] & ((1u << lane) - 1u));
+          t_x[dst] = sx[k]; t_y[dst] = sy[k]; t_z[dst] = sz[k];
+          if (!UNIFORM_H) t_h[dst] = sh[k];
+          t_pos[dst] = sq[k]; t_dem[dst] = sd[k];
+        }
+      }
+      tile_cnt = run;
+      it++;
     }
   }
   phase_a();
 
-  // ---- 4. phase B: slots ---------------------------------------------------
+  // ---- 4. phase B: slots, ascending source dem_id --------------------------
   double fx = 0, fy = 0, fz = 0;
   unsigned nactive = 0;
   if (valid) {
@@ -184,51 +247,23 @@ k_contact(RbxScene S, RbxCells C, RbxParams P, RbxDiag D, double reach, double h
     const double ud = S.u[p], vd = S.v[p], wd = S.w[p];
     const double spacing0 = S.spacing0[body];
     fx = md * P.gx; fy = md * P.gy; fz = md * P.gz;  // BodyForce :122-125
+    unsigned st = list_overflow ? RBX_STATUS_LIST_OVERFLOW : 0u;
 
-    // distinct source bodies, ascending (registers, static indexing)
-    int keys[RBX_MAX_KEYS];
-#pragma unroll
-    for (int k = 0; k < RBX_MAX_KEYS; k++) keys[k] = 0x7fffffff;
-    int nk = 0;
-    bool key_overflow = false;
-    for (int e = 0; e < nlist; e++) {
-      const int d = l_dem[e];
-      bool found = false;
-#pragma unroll
-      for (int k = 0; k < RBX_MAX_KEYS; k++) found |= (keys[k] == d);
-      if (!found) {
-        if (nk < RBX_MAX_KEYS) {
-#pragma unroll
-          for (int k = 0; k < RBX_MAX_KEYS; k++) if (k == nk) keys[k] = d;
-          nk++;
-        } else {
-          key_overflow = true;
-        }
-      }
-    }
-#pragma unroll
-    for (int a = 0; a < RBX_MAX_KEYS - 1; a++)
-#pragma unroll
-      for (int b = 0; b < RBX_MAX_KEYS - 1 - a; b++) {
-        int lo = min(keys[b], keys[b + 1]), hi = max(keys[b], keys[b + 1]);
-        keys[b] = lo; keys[b + 1] = hi;
-      }
-    unsigned st = 0;
-    if (key_overflow) st |= RBX_STATUS_SLOT_OVERFLOW;
-    if (list_overflow) st |= RBX_STATUS_LIST_OVERFLOW;
-
-    int nout = 0;
-    for (int ki = 0; ki < nk; ki++) {
-      int key = 0;
-#pragma unroll
-      for (int k = 0; k < RBX_MAX_KEYS; k++) if (k == ki) key = keys[k];
-
+    int key = 0x7fffffff;
+    for (int e = 0; e < nlist; e++) key = min(key, l_dem[e]);
+    int nout = 0, ki = 0;
+    while (key != 0x7fffffff) {
+      int next = 0x7fffffff;
       SlotAcc a;
       a.ax = a.ay = a.az = a.w1 = a.bx = a.by = a.bz = a.w2 = 0.;
       a.rmin = 4. * spacing0;  // :765
       a.pmin = -1; a.gmin = 0x7fffffff;
       for (int e = 0; e < nlist; e++) {
-        if (l_dem[e] != key) continue;
+        const int d = l_dem[e];
+        if (d != key) {
+          if (d > key && d < next) next = d;
+          continue;
+        }
         const int q = l_pos[e];
         const double x0 = px - C.sx[q], x1 = py - C.sy[q], x2 = pz - C.sz[q];
         const double rij = sqrt(rbx_r2(x0, x1, x2));
@@ -331,18 +366,24 @@ k_contact(RbxScene S, RbxCells C, RbxParams P, RbxDiag D, double reach, double h
         }
       }
       if (D.key) {
-        const size_t o = (size_t)ki * n_rigid + p;
-        D.key[o] = key;
-        if (D.closest) D.closest[o] = a.pmin >= 0 ? a.gmin : -1;
-        if (D.nx) { D.nx[o] = nx; D.ny[o] = ny; D.nz[o] = nz; }
-        if (D.dist) D.dist[o] = dist;
-        if (D.overlap) D.overlap[o] = ovl_out;
-        if (D.ftx) { D.ftx[o] = ft0; D.fty[o] = ft1; D.ftz[o] = ft2; }
+        if (ki < RBX_MAX_KEYS) {
+          const size_t o = (size_t)ki * n_rigid + p;
+          D.key[o] = key;
+          if (D.closest) D.closest[o] = a.pmin >= 0 ? a.gmin : -1;
+          if (D.nx) { D.nx[o] = nx; D.ny[o] = ny; D.nz[o] = nz; }
+          if (D.dist) D.dist[o] = dist;
+          if (D.overlap) D.overlap[o] = ovl_out;
+          if (D.ftx) { D.ftx[o] = ft0; D.fty[o] = ft1; D.ftz[o] = ft2; }
+        } else {
+          st |= RBX_STATUS_SLOT_OVERFLOW;
+        }
       }
+      ki++;
+      key = next;
     }
     if (nout < S.ks) S.hist_key_out[(size_t)nout * n_rigid + p] = -1;
     if (D.key)
-      for (int ki = nk; ki < RBX_MAX_KEYS; ki++) D.key[(size_t)ki * n_rigid + p] = -1;
+      for (int k2 = ki; k2 < RBX_MAX_KEYS; k2++) D.key[(size_t)k2 * n_rigid + p] = -1;
     if (st && S.status) atomicOr(S.status, st);
     S.fx[p] = fx; S.fy[p] = fy; S.fz[p] = fz;
   }
@@ -381,7 +422,7 @@ k_contact(RbxScene S, RbxCells C, RbxParams P, RbxDiag D, double reach, double h
   if (tid < 6) {
     double s = red[0][tid];
 #pragma unroll
-    for (int w2 = 1; w2 < RBX_CHUNK / 32; w2++) s += red[w2][tid];
+    for (int w2 = 1; w2 < kWarps; w2++) s += red[w2][tid];
     S.chunk_ft[(size_t)chunk * 6 + tid] = s;
   }
   if (tid < 3 && S.counters) atomicAdd(&S.counters[tid], cnt_s[tid]);

@@ -53,7 +53,7 @@ def _ptr(t):
 class DeviceScene(object):
     def __init__(self, arrays, rigid_names, boundary_names=(), dim=3,
                  kr=1e5, kf=1e3, fric_coeff=0.5, gx=0., gy=0., gz=0.,
-                 planar=False, ks=4, radius_scale=3.0, eta_uniform=None,
+                 planar=False, ks=8, radius_scale=3.0, eta_uniform=None,
                  cap_cells=None, device=None):
         if not torch.cuda.is_available():
             raise _lib.RbxError('DeviceScene needs a CUDA device; the '
