@@ -42,7 +42,8 @@ typedef enum {
 } RbxError;
 
 /* bits of the device status word */
-#define RBX_STATUS_SLOT_OVERFLOW 1u  /* diagnostics only: > RBX_MAX_KEYS slots */
+#define RBX_STATUS_SLOT_OVERFLOW 1u  /* > 32 bodies touch one particle (or the
+                                        diagnostics hold > RBX_MAX_KEYS)   */
 #define RBX_STATUS_HIST_OVERFLOW 2u  /* > ks simultaneous contacts            */
 #define RBX_STATUS_LIST_OVERFLOW 4u  /* per-particle neighbour list full       */
 #define RBX_STATUS_GRID_COARSENED 8u /* cell size enlarged to fit cap_cells    */
@@ -99,6 +100,8 @@ typedef struct {
   int32_t ks;        /* history slots per particle                         */
   int32_t eta_mode;  /* 0: none, 1: dense table rows, 2: uniform scalar    */
   int32_t planar;    /* 1: GTVFRigidBody2DStep semantics                   */
+  int32_t list_cap;  /* neighbour-list entries per particle                */
+  int32_t pad_;
   /* per particle [n_total] */
   double *x, *y, *z, *u, *v, *w;
   const double *h, *m, *rho;
@@ -114,7 +117,13 @@ typedef struct {
   const int32_t *chunk_start; /* [n_chunks + 1] particle ranges          */
   const int32_t *chunk_body;  /* [n_chunks]                              */
   const int32_t *body_chunk;  /* [n_bodies + 1] chunk ranges per body    */
-  double *chunk_ft;           /* [n_chunks * 6] partial force, torque    */
+  double *chunk_ft;           /* [n_chunks * 4 * 6] per-warp partial
+                                 force, torque                           */
+  /* in-range gated neighbours, [list_cap][n_rigid]: sorted position in the
+   * cell list and source dem_id; nbr_cnt[n_rigid] entries per particle.
+   * Written and read inside rbx_contact_mofidi (scratch between its two
+   * launches). */
+  int32_t *nbr_pos, *nbr_dem, *nbr_cnt;
   /* per body */
   const double *total_mass, *izz, *spacing0; /* [n_bodies]               */
   double *xcm, *vcm, *ang_mom, *omega;       /* [3 n_bodies]             */

@@ -116,7 +116,8 @@ __global__ void k_bodies(RbxScene S, int mode, double dt) {
   const int b = warp;
   if (mode & 1) {
     double v6[6] = {0, 0, 0, 0, 0, 0};
-    const int c0 = S.body_chunk[b], c1 = S.body_chunk[b + 1];
+    // four warp partials per chunk (rbx_contact.cu, k_slots)
+    const int c0 = 4 * S.body_chunk[b], c1 = 4 * S.body_chunk[b + 1];
     for (int c = c0 + lane; c < c1; c += 32) {
 #pragma unroll
       for (int a = 0; a < 6; a++) v6[a] += S.chunk_ft[(size_t)c * 6 + a];

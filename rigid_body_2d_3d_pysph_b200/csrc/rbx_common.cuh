@@ -6,8 +6,7 @@
 #include "rbx.h"
 
 #define RBX_CHUNK 128     // threads per CTA = max particles per work item
-#define RBX_TILE 1024     // staged source particles per shared-memory tile
-#define RBX_LISTCAP 160   // in-range gated neighbours kept per particle
+#define RBX_TILE 768      // staged source particles per shared-memory tile
 
 #define RBX_CHECK_LAUNCH()                                   \
   do {                                                       \

@@ -1,29 +1,34 @@
 // Fused Mofidi-style contact evaluation with sparse (particle, source body)
-// slots.  Replaces, in one launch, the five equation groups wired at
+// slots.  Replaces the five equation groups wired at
 // /root/reference/code/rigid_body_3d.py:641-698:
 //   ComputeContactForceNormals                  rigid_body_common.py:631-723
 //   ComputeContactForceDistanceAndClosestPoint  rigid_body_common.py:726-836
 //   BodyForce.initialize                        rigid_body_common.py:115-125
 //   ComputeContactForce.post_loop               rigid_body_common.py:839-1032
-//   SumUpExternalForces.reduce (chunk partials) rigid_body_common.py:128-175
+//   SumUpExternalForces.reduce (warp partials)  rigid_body_common.py:128-175
 //
-// Work decomposition: one CTA per "chunk" (<= 128 consecutive particles of
-// one rigid body).  The CTA
+// Two launches over the same decomposition: one CTA per "chunk" (<= 128
+// consecutive particles of one rigid body, thread t <-> particle p0 + t).
+//
+// k_neighbours (FP64-pipe bound; shared-memory staged)
 //   1. reduces the chunk's bounding box,
 //   2. streams the cell-list rows overlapping box +- reach (coalesced SoA
-//      loads), drops the body's own particles and everything outside the
-//      box, and compacts the rest into a shared-memory tile (deterministic
-//      ballot/prefix compaction, no atomics),
-//   3. phase A: every thread tests its particle against the tile (broadcast
-//      shared-memory reads, exact FP64 predicate) and appends hits to a
-//      private neighbour list,
-//   4. phase B: per distinct source body (ascending dem_id) the thread
-//      accumulates the slot sums in registers -- single pass: the distance
-//      sum of pass 2 is n . sum(XIJ m/rho W), so the reference's two pair
-//      loops collapse into one -- then applies the spring/dashpot/Coulomb
-//      law with the history carried in the sparse slot table,
-//   5. warp-shuffle + shared-memory reduction of force and torque about the
-//      body's centre of mass -> one partial per chunk (fixed order).
+//      loads, 4 independent loads per thread per barrier), drops the body's
+//      own particles and everything outside the box, and compacts the rest
+//      into a shared-memory tile (deterministic ballot/prefix compaction),
+//   3. every thread tests its particle against the tile (broadcast
+//      shared-memory reads, exact FP64 predicate) and appends the hits to
+//      its neighbour list in HBM, laid out [entry][particle] so that both
+//      this write and the later read coalesce.
+// k_slots (latency bound; no shared memory, no block barriers)
+//   4. per distinct source body (ascending dem_id) the thread accumulates
+//      the slot sums in registers, four list entries in flight at a time --
+//      single pass: the distance sum of pass 2 is n . sum(XIJ m/rho W), so
+//      the reference's two pair loops collapse into one -- then applies the
+//      spring/dashpot/Coulomb law with the history carried in the sparse
+//      slot table,
+//   5. warp-shuffle reduction of force and torque about the body's centre of
+//      mass -> one partial per warp (fixed order, deterministic).
 #include "rbx_common.cuh"
 #include <string.h>
 
@@ -39,10 +44,11 @@ struct SlotAcc {
 
 constexpr int kWarps = RBX_CHUNK / 32;
 constexpr int kBatch = 4;   // staged candidates per thread per iteration
+constexpr int kPre = 4;     // list entries in flight per thread in k_slots
 
-template <int DIM, bool UNIFORM_H>
-__global__ void __launch_bounds__(RBX_CHUNK, 4)
-k_contact(RbxScene S, RbxCells C, RbxParams P, RbxDiag D, double reach, double h_uniform) {
+template <bool UNIFORM_H>
+__global__ void __launch_bounds__(RBX_CHUNK, 6)
+k_neighbours(RbxScene S, RbxCells C, RbxParams P, double reach, double h_uniform) {
   __shared__ double t_x[RBX_TILE], t_y[RBX_TILE], t_z[RBX_TILE];
   __shared__ double t_h[UNIFORM_H ? 1 : RBX_TILE];
   __shared__ int t_pos[RBX_TILE], t_dem[RBX_TILE];
@@ -51,17 +57,15 @@ k_contact(RbxScene S, RbxCells C, RbxParams P, RbxDiag D, double reach, double h
   __shared__ int row_s[RBX_CHUNK], row_off[RBX_CHUNK + 1];
   __shared__ int wscan[kWarps];
   __shared__ int range[6];
-  __shared__ unsigned long long cnt_s[3];
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int chunk = blockIdx.x;
   const int p0 = S.chunk_start[chunk], p1 = S.chunk_start[chunk + 1];
   const int p = p0 + tid;
   const bool valid = p < p1;
-  const int body = S.chunk_body[chunk];
   const int my_dem = S.dem_id[p0];
   const RbxGridInfo gi = *C.info;
-  const int n_rigid = S.n_rigid;
+  const size_t n_rigid = (size_t)S.n_rigid;
 
   double px = 0, py = 0, pz = 0, ph = 0;
   if (valid) { px = S.x[p]; py = S.y[p]; pz = S.z[p]; ph = S.h[p]; }
@@ -76,7 +80,6 @@ k_contact(RbxScene S, RbxCells C, RbxParams P, RbxDiag D, double reach, double h
 #pragma unroll
       for (int a = 0; a < 3; a++) { red[wid][a] = lo[a]; red[wid][3 + a] = hi[a]; }
     }
-    if (tid < 3) cnt_s[tid] = 0ull;
     __syncthreads();
   }
   double blo[3], bhi[3];
@@ -105,12 +108,10 @@ k_contact(RbxScene S, RbxCells C, RbxParams P, RbxDiag D, double reach, double h
   const int nry = cy1 - cy0 + 1;
   const int nrows = nry * (cz1 - cz0 + 1);
 
-  // ---- per-thread neighbour list (local memory, L1 resident) -------------
-  int l_pos[RBX_LISTCAP];
-  int l_dem[RBX_LISTCAP];
   int nlist = 0;
   bool list_overflow = false;
   unsigned long long ncand = 0;
+  const int cap = S.list_cap;
 
   const double rs2 = P.radius_scale * P.radius_scale;
   const double hi2 = rbx_h2(rs2, ph);
@@ -119,19 +120,21 @@ k_contact(RbxScene S, RbxCells C, RbxParams P, RbxDiag D, double reach, double h
   int tile_cnt = 0;
   int it = 0;
 
+  // ---- 3. exact predicate against the staged tile -------------------------
   auto phase_a = [&]() {
     __syncthreads();  // tile complete
     if (valid) {
       ncand += (unsigned long long)tile_cnt;
+#pragma unroll 4
       for (int j = 0; j < tile_cnt; j++) {
         const double r2 = rbx_r2(px - t_x[j], py - t_y[j], pz - t_z[j]);
         bool hit = r2 < hi2;
         if (!UNIFORM_H) hit = hit || (r2 < rbx_h2(rs2, t_h[j]));
         else hit = hit || (r2 < hj2_u);
         if (hit) {
-          if (nlist < RBX_LISTCAP) {
-            l_pos[nlist] = t_pos[j];
-            l_dem[nlist] = t_dem[j];
+          if (nlist < cap) {
+            S.nbr_pos[(size_t)nlist * n_rigid + p] = t_pos[j];
+            S.nbr_dem[(size_t)nlist * n_rigid + p] = t_dem[j];
             nlist++;
           } else {
             list_overflow = true;
@@ -143,7 +146,7 @@ k_contact(RbxScene S, RbxCells C, RbxParams P, RbxDiag D, double reach, double h
     tile_cnt = 0;
   };
 
-  // ---- 2./3. stage the cell rows overlapping the box ----------------------
+  // ---- 2. stage the cell rows overlapping the box --------------------------
   // Rows (cy, cz) are contiguous index ranges of the sorted arrays.  All row
   // bounds are fetched at once (one row per thread), prefix-summed into one
   // flat candidate sequence, and that sequence is streamed kBatch*128
@@ -239,147 +242,282 @@ k_contact(RbxScene S, RbxCells C, RbxParams P, RbxDiag D, double reach, double h
   }
   phase_a();
 
-  // ---- 4. phase B: slots, ascending source dem_id --------------------------
-  double fx = 0, fy = 0, fz = 0;
+  if (valid) {
+    S.nbr_cnt[p] = nlist;
+    if (list_overflow && S.status) atomicOr(S.status, RBX_STATUS_LIST_OVERFLOW);
+  }
+  // counters: gated in-range pairs, candidate tests
+  if (S.counters) {
+    unsigned long long g = (unsigned long long)nlist, c = ncand;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      g += __shfl_xor_sync(0xffffffffu, g, o);
+      c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+    if (lane == 0) { atomicAdd(&S.counters[0], g); atomicAdd(&S.counters[2], c); }
+  }
+}
+
+constexpr int kAcc = 4;     // slots accumulated per pass over the list
+constexpr int kFields = 10; // ax ay az w1 bx by bz w2 rmin (pmin,gmin)
+
+template <int DIM, bool UNIFORM_H>
+__global__ void __launch_bounds__(RBX_CHUNK, 4)
+k_slots(RbxScene S, RbxCells C, RbxParams P, RbxDiag D, double h_uniform) {
+  // slot accumulators: [slot][field][thread] -> conflict-free, no dynamic
+  // register indexing.  Field 9 packs (pmin, gmin) as two ints.
+  __shared__ double acc[kAcc][kFields][RBX_CHUNK];
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int chunk = blockIdx.x;
+  const int p0 = S.chunk_start[chunk], p1 = S.chunk_start[chunk + 1];
+  if (p0 + wid * 32 >= p1) {   // whole warp beyond the chunk: zero partial
+    if (lane < 6) S.chunk_ft[((size_t)chunk * kWarps + wid) * 6 + lane] = 0.;
+    return;
+  }
+  const int p = p0 + tid;
+  const bool valid = p < p1;
+  const int body = S.chunk_body[chunk];
+  const size_t n_rigid = (size_t)S.n_rigid;
+
+  double fx = 0, fy = 0, fz = 0, px = 0, py = 0, pz = 0;
   unsigned nactive = 0;
   if (valid) {
+    px = S.x[p]; py = S.y[p]; pz = S.z[p];
+    const double ph = S.h[p];
     const double md = S.m[p], rhod = S.rho[p];
     const double ud = S.u[p], vd = S.v[p], wd = S.w[p];
     const double spacing0 = S.spacing0[body];
+    const int nlist = S.nbr_cnt[p];
+    const int* __restrict__ lpos = S.nbr_pos + p;
+    const int* __restrict__ ldem = S.nbr_dem + p;
     fx = md * P.gx; fy = md * P.gy; fz = md * P.gz;  // BodyForce :122-125
-    unsigned st = list_overflow ? RBX_STATUS_LIST_OVERFLOW : 0u;
+    unsigned st = 0u;
+    const double hij_u = 0.5 * (ph + h_uniform);
+    const double rmin0 = 4. * spacing0;              // :765
 
-    int key = 0x7fffffff;
-    for (int e = 0; e < nlist; e++) key = min(key, l_dem[e]);
     int nout = 0, ki = 0;
-    while (key != 0x7fffffff) {
-      int next = 0x7fffffff;
-      SlotAcc a;
-      a.ax = a.ay = a.az = a.w1 = a.bx = a.by = a.bz = a.w2 = 0.;
-      a.rmin = 4. * spacing0;  // :765
-      a.pmin = -1; a.gmin = 0x7fffffff;
-      for (int e = 0; e < nlist; e++) {
-        const int d = l_dem[e];
-        if (d != key) {
-          if (d > key && d < next) next = d;
-          continue;
+    // A particle touching more than kAcc bodies takes further rounds; the
+    // keys already served are remembered here (rare path, local memory).
+    int served[32];
+    int n_served = 0;
+    bool more = nlist > 0;
+    while (more) {
+      more = false;
+      // ---- one pass over the list: every entry's pair math runs once and
+      //      lands in the accumulator of its source body --------------------
+      int keys[kAcc];
+#pragma unroll
+      for (int k = 0; k < kAcc; k++) keys[k] = 0x7fffffff;
+      int nk = 0;
+      bool overflow = false;       // some key did not fit this round
+      for (int e0 = 0; e0 < nlist; e0 += kPre) {
+        int dd[kPre], qq[kPre];
+        double sx[kPre], sy[kPre], sz[kPre], sh[kPre];
+#pragma unroll
+        for (int k = 0; k < kPre; k++) {
+          const int e = e0 + k;
+          const bool in = e < nlist;
+          dd[k] = in ? ldem[(size_t)e * n_rigid] : -1;
+          qq[k] = in ? lpos[(size_t)e * n_rigid] : 0;
         }
-        const int q = l_pos[e];
-        const double x0 = px - C.sx[q], x1 = py - C.sy[q], x2 = pz - C.sz[q];
-        const double rij = sqrt(rbx_r2(x0, x1, x2));
-        const double hij = 0.5 * (ph + (UNIFORM_H ? h_uniform : C.sh[q]));
-        const double wij = rbx_quintic<DIM>(rij, hij);
-        const double tmp1 = md / (rhod * rij) * wij;   // :683
-        a.ax += x0 * tmp1; a.ay += x1 * tmp1; a.az += x2 * tmp1;
-        a.w1 += tmp1 * rij;                            // :690
-        const double tmp2 = md / (rhod) * wij;         // :803
-        a.bx += x0 * tmp2; a.by += x1 * tmp2; a.bz += x2 * tmp2;
-        a.w2 += tmp2;                                  // :809
-        if (rij <= a.rmin) {                           // :811 (+ tie rule Q6)
-          const int g = C.gidx[q];
-          if (rij < a.rmin || (a.pmin >= 0 && g < a.gmin)) {
-            a.rmin = rij; a.pmin = q; a.gmin = g;
+        if (n_served) {
+#pragma unroll
+          for (int k = 0; k < kPre; k++)
+            for (int j = 0; j < n_served; j++) if (served[j] == dd[k]) dd[k] = -1;
+        }
+#pragma unroll
+        for (int k = 0; k < kPre; k++) {
+          if (dd[k] >= 0) {
+            sx[k] = C.sx[qq[k]]; sy[k] = C.sy[qq[k]]; sz[k] = C.sz[qq[k]];
+            if (!UNIFORM_H) sh[k] = C.sh[qq[k]];
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < kPre; k++) {
+          const int d = dd[k];
+          if (d < 0) continue;
+          // slot of this key (first come, first served)
+          int sl = -1;
+#pragma unroll
+          for (int j = 0; j < kAcc; j++) if (keys[j] == d) sl = j;
+          if (sl < 0) {
+            if (nk < kAcc) {
+              sl = nk;
+#pragma unroll
+              for (int j = 0; j < kAcc; j++) if (j == nk) keys[j] = d;
+              nk++;
+#pragma unroll
+              for (int f = 0; f < 8; f++) acc[sl][f][tid] = 0.;
+              acc[sl][8][tid] = rmin0;
+              reinterpret_cast<int2 *>(&acc[sl][9][tid])[0] = make_int2(-1, 0x7fffffff);
+            } else {
+              overflow = true;
+              continue;
+            }
+          }
+          const double x0 = px - sx[k], x1 = py - sy[k], x2 = pz - sz[k];
+          const double rij = sqrt(rbx_r2(x0, x1, x2));
+          const double hij = UNIFORM_H ? hij_u : 0.5 * (ph + sh[k]);
+          const double wij = rbx_quintic<DIM>(rij, hij);
+          const double tmp1 = md / (rhod * rij) * wij;   // :683
+          const double tmp2 = md / (rhod) * wij;         // :803
+          acc[sl][0][tid] += x0 * tmp1;                  // :686-688
+          acc[sl][1][tid] += x1 * tmp1;
+          acc[sl][2][tid] += x2 * tmp1;
+          acc[sl][3][tid] += tmp1 * rij;                 // :690
+          acc[sl][4][tid] += x0 * tmp2;                  // :807 (n . sum)
+          acc[sl][5][tid] += x1 * tmp2;
+          acc[sl][6][tid] += x2 * tmp2;
+          acc[sl][7][tid] += tmp2;                       // :809
+          const double rmin = acc[sl][8][tid];
+          if (rij <= rmin) {                             // :811 (+ tie rule Q6)
+            const int2 pg = reinterpret_cast<int2 *>(&acc[sl][9][tid])[0];
+            const int g = C.gidx[qq[k]];
+            if (rij < rmin || (pg.x >= 0 && g < pg.y)) {
+              acc[sl][8][tid] = rij;
+              reinterpret_cast<int2 *>(&acc[sl][9][tid])[0] = make_int2(qq[k], g);
+            }
           }
         }
       }
-      // ComputeContactForceNormals.post_loop :705-723
-      double nx = 0., ny = 0., nz = 0.;
-      if (a.w1 > 1e-12) {
-        nx = a.ax / a.w1; ny = a.ay / a.w1; nz = a.az / a.w1;
-        const double magn = sqrt(nx * nx + ny * ny + nz * nz);
-        nx /= magn; ny /= magn; nz /= magn;
-      }
-      // ...DistanceAndClosestPoint.post_loop :829-836, with
-      // dist_tmp = sum (n.XIJ) tmp2 = n . sum XIJ tmp2
-      double dist = 0.;
-      if (a.w2 > 1e-12) dist = (nx * a.bx + ny * a.by + nz * a.bz) / a.w2;
-      double vxs = 0., vys = 0., vzs = 0.;
-      if (a.pmin >= 0) { vxs = S.u[a.gmin]; vys = S.v[a.gmin]; vzs = S.w[a.gmin]; }
-
-      // previous state of this slot
-      double dl0 = 0., dl1 = 0., dl2 = 0., fn0 = 0., fn1 = 0., fn2 = 0.;
-      for (int s = 0; s < S.ks; s++) {
-        const int hk = S.hist_key_in[(size_t)s * n_rigid + p];
-        if (hk < 0) break;
-        if (hk == key) {
-          const size_t o = (size_t)s * n_rigid + p, pl = (size_t)S.ks * n_rigid;
-          dl0 = S.hist_dlt_in[o]; dl1 = S.hist_dlt_in[pl + o]; dl2 = S.hist_dlt_in[2 * pl + o];
-          fn0 = S.hist_fn_in[o]; fn1 = S.hist_fn_in[pl + o]; fn2 = S.hist_fn_in[2 * pl + o];
-          break;
+      // ---- finalize this round's slots in ascending key order -------------
+      int ord[kAcc];
+#pragma unroll
+      for (int k = 0; k < kAcc; k++) ord[k] = k;
+#pragma unroll
+      for (int a2 = 0; a2 < kAcc - 1; a2++)
+#pragma unroll
+        for (int b2 = 0; b2 < kAcc - 1 - a2; b2++) {
+          const bool sw = keys[b2] > keys[b2 + 1];
+          const int k0 = sw ? keys[b2 + 1] : keys[b2], k1 = sw ? keys[b2] : keys[b2 + 1];
+          const int o0 = sw ? ord[b2 + 1] : ord[b2], o1 = sw ? ord[b2] : ord[b2 + 1];
+          keys[b2] = k0; keys[b2 + 1] = k1; ord[b2] = o0; ord[b2 + 1] = o1;
         }
-      }
+      for (int kk = 0; kk < nk; kk++) {
+        int key = 0, sl = 0;
+#pragma unroll
+        for (int j = 0; j < kAcc; j++) if (j == kk) { key = keys[j]; sl = ord[j]; }
+        const double a_ax = acc[sl][0][tid], a_ay = acc[sl][1][tid], a_az = acc[sl][2][tid];
+        const double a_w1 = acc[sl][3][tid];
+        const double a_bx = acc[sl][4][tid], a_by = acc[sl][5][tid], a_bz = acc[sl][6][tid];
+        const double a_w2 = acc[sl][7][tid];
+        const int2 pg = reinterpret_cast<int2 *>(&acc[sl][9][tid])[0];
+        // ComputeContactForceNormals.post_loop :705-723
+        double nx = 0., ny = 0., nz = 0.;
+        if (a_w1 > 1e-12) {
+          nx = a_ax / a_w1; ny = a_ay / a_w1; nz = a_az / a_w1;
+          const double magn = sqrt(nx * nx + ny * ny + nz * nz);
+          nx /= magn; ny /= magn; nz /= magn;
+        }
+        // ...DistanceAndClosestPoint.post_loop :829-836, with
+        // dist_tmp = sum (n.XIJ) tmp2 = n . sum XIJ tmp2
+        double dist = 0.;
+        if (a_w2 > 1e-12) dist = (nx * a_bx + ny * a_by + nz * a_bz) / a_w2;
+        double vxs = 0., vys = 0., vzs = 0.;
+        if (pg.x >= 0) { vxs = S.u[pg.y]; vys = S.v[pg.y]; vzs = S.w[pg.y]; }
 
-      // ComputeContactForce.post_loop :906-1032
-      double ovl_out = 0., ft0 = 0., ft1 = 0., ft2 = 0.;
-      const double overlap = spacing0 - dist;
-      bool active = false;
-      if (overlap > 0. && overlap != spacing0) {
-        active = true;
-        const double vij_x = ud - vxs, vij_y = vd - vys, vij_z = wd - vzs;
-        const double vn = vij_x * nx + vij_y * ny + vij_z * nz;
-        ovl_out = overlap;
-        const double tmp = P.kr * overlap;
-        double eta = 0.;
-        if (S.eta_mode == 1) eta = S.eta[S.eta_row[body] + key];       // :925
-        else if (S.eta_mode == 2) eta = S.eta[0];
-        eta = eta * sqrt(md / 2. * P.kr);                               // :926
-        const double fnx = (tmp - eta * vn) * nx;
-        const double fny = (tmp - eta * vn) * ny;
-        const double fnz = (tmp - eta * vn) * nz;
-        const double vij_magn = sqrt(vij_x * vij_x + vij_y * vij_y + vij_z * vij_z);
-        if (vij_magn < 1e-12) {
-          dl0 = dl1 = dl2 = 0.;   // fn (fn0..2) keeps its previous value: Q3
+        // previous state of this slot
+        double dl0 = 0., dl1 = 0., dl2 = 0., fn0 = 0., fn1 = 0., fn2 = 0.;
+        for (int s2 = 0; s2 < S.ks; s2++) {
+          const int hk = S.hist_key_in[(size_t)s2 * n_rigid + p];
+          if (hk < 0) break;
+          if (hk == key) {
+            const size_t o = (size_t)s2 * n_rigid + p, pl = (size_t)S.ks * n_rigid;
+            dl0 = S.hist_dlt_in[o]; dl1 = S.hist_dlt_in[pl + o]; dl2 = S.hist_dlt_in[2 * pl + o];
+            fn0 = S.hist_fn_in[o]; fn1 = S.hist_fn_in[pl + o]; fn2 = S.hist_fn_in[2 * pl + o];
+            break;
+          }
+        }
+
+        // ComputeContactForce.post_loop :906-1032
+        double ovl_out = 0., ft0 = 0., ft1 = 0., ft2 = 0.;
+        const double overlap = spacing0 - dist;
+        bool active = false;
+        if (overlap > 0. && overlap != spacing0) {
+          active = true;
+          const double vij_x = ud - vxs, vij_y = vd - vys, vij_z = wd - vzs;
+          const double vn = vij_x * nx + vij_y * ny + vij_z * nz;
+          ovl_out = overlap;
+          const double tmp = P.kr * overlap;
+          double eta = 0.;
+          if (S.eta_mode == 1) eta = S.eta[S.eta_row[body] + key];       // :925
+          else if (S.eta_mode == 2) eta = S.eta[0];
+          eta = eta * sqrt(md / 2. * P.kr);                               // :926
+          const double fnx = (tmp - eta * vn) * nx;
+          const double fny = (tmp - eta * vn) * ny;
+          const double fnz = (tmp - eta * vn) * nz;
+          const double vij_magn = sqrt(vij_x * vij_x + vij_y * vij_y + vij_z * vij_z);
+          if (vij_magn < 1e-12) {
+            dl0 = dl1 = dl2 = 0.;   // fn (fn0..2) keeps its previous value: Q3
+          } else {
+            const double tx = vij_x - nx * vn, ty = vij_y - ny * vn, tz = vij_z - nz * vn;
+            const double ti_magn = sqrt(tx * tx + ty * ty + tz * tz);
+            double ti_x = 0., ti_y = 0., ti_z = 0.;
+            if (ti_magn > 1e-12) { ti_x = tx / ti_magn; ti_y = ty / ti_magn; ti_z = tz / ti_magn; }
+            const double sx_ = dl0 + vij_x * P.dt, sy_ = dl1 + vij_y * P.dt, sz_ = dl2 + vij_z * P.dt;
+            const double ddt = sx_ * ti_x + sy_ * ti_y + sz_ * ti_z;
+            dl0 = ddt * ti_x; dl1 = ddt * ti_y; dl2 = ddt * ti_z;
+            const double fsx = -P.kf * dl0, fsy = -P.kf * dl1, fsz = -P.kf * dl2;
+            const double ft_magn = sqrt(fsx * fsx + fsy * fsy + fsz * fsz);
+            const double fn_magn = sqrt(fnx * fnx + fny * fny + fnz * fnz);
+            const double ca = P.fric_coeff * fn_magn;
+            const double ft_star = (ft_magn < ca) ? ft_magn : ca;  // (b<a)?b:a, App. C-7
+            ft0 = -ft_star * ti_x; ft1 = -ft_star * ti_y; ft2 = -ft_star * ti_z;
+            const double mx = -ft0 / P.kf, my = -ft1 / P.kf, mz = -ft2 / P.kf;
+            const double lt = sqrt(mx * mx + my * my + mz * mz);
+            dl0 = mx / lt; dl1 = my / lt; dl2 = mz / lt;            // Q1, Q2 (0/0 = NaN)
+            fn0 = fnx; fn1 = fny; fn2 = fnz;
+          }
         } else {
-          const double tx = vij_x - nx * vn, ty = vij_y - ny * vn, tz = vij_z - nz * vn;
-          const double ti_magn = sqrt(tx * tx + ty * ty + tz * tz);
-          double ti_x = 0., ti_y = 0., ti_z = 0.;
-          if (ti_magn > 1e-12) { ti_x = tx / ti_magn; ti_y = ty / ti_magn; ti_z = tz / ti_magn; }
-          const double sx_ = dl0 + vij_x * P.dt, sy_ = dl1 + vij_y * P.dt, sz_ = dl2 + vij_z * P.dt;
-          const double ddt = sx_ * ti_x + sy_ * ti_y + sz_ * ti_z;
-          dl0 = ddt * ti_x; dl1 = ddt * ti_y; dl2 = ddt * ti_z;
-          const double fsx = -P.kf * dl0, fsy = -P.kf * dl1, fsz = -P.kf * dl2;
-          const double ft_magn = sqrt(fsx * fsx + fsy * fsy + fsz * fsz);
-          const double fn_magn = sqrt(fnx * fnx + fny * fny + fnz * fnz);
-          const double ca = P.fric_coeff * fn_magn;
-          const double ft_star = (ft_magn < ca) ? ft_magn : ca;  // (b<a)?b:a, App. C-7
-          ft0 = -ft_star * ti_x; ft1 = -ft_star * ti_y; ft2 = -ft_star * ti_z;
-          const double mx = -ft0 / P.kf, my = -ft1 / P.kf, mz = -ft2 / P.kf;
-          const double lt = sqrt(mx * mx + my * my + mz * mz);
-          dl0 = mx / lt; dl1 = my / lt; dl2 = mz / lt;            // Q1, Q2 (0/0 = NaN)
-          fn0 = fnx; fn1 = fny; fn2 = fnz;
+          dl0 = dl1 = dl2 = 0.; fn0 = fn1 = fn2 = 0.;
         }
-      } else {
-        dl0 = dl1 = dl2 = 0.; fn0 = fn1 = fn2 = 0.;
-      }
-      fx += fn0 + ft0; fy += fn1 + ft1; fz += fn2 + ft2;         // :1030-1032
+        fx += fn0 + ft0; fy += fn1 + ft1; fz += fn2 + ft2;         // :1030-1032
 
-      if (active) {
-        nactive++;
-        if (nout < S.ks) {
-          const size_t o = (size_t)nout * n_rigid + p, pl = (size_t)S.ks * n_rigid;
-          S.hist_key_out[o] = key;
-          S.hist_dlt_out[o] = dl0; S.hist_dlt_out[pl + o] = dl1; S.hist_dlt_out[2 * pl + o] = dl2;
-          S.hist_fn_out[o] = fn0; S.hist_fn_out[pl + o] = fn1; S.hist_fn_out[2 * pl + o] = fn2;
-          nout++;
-        } else {
-          st |= RBX_STATUS_HIST_OVERFLOW;
+        if (active) {
+          nactive++;
+          if (nout < S.ks) {
+            const size_t o = (size_t)nout * n_rigid + p, pl = (size_t)S.ks * n_rigid;
+            S.hist_key_out[o] = key;
+            S.hist_dlt_out[o] = dl0; S.hist_dlt_out[pl + o] = dl1; S.hist_dlt_out[2 * pl + o] = dl2;
+            S.hist_fn_out[o] = fn0; S.hist_fn_out[pl + o] = fn1; S.hist_fn_out[2 * pl + o] = fn2;
+            nout++;
+          } else {
+            st |= RBX_STATUS_HIST_OVERFLOW;
+          }
         }
+        if (D.key) {
+          if (ki < RBX_MAX_KEYS) {
+            const size_t o = (size_t)ki * n_rigid + p;
+            D.key[o] = key;
+            if (D.closest) D.closest[o] = pg.x >= 0 ? pg.y : -1;
+            if (D.nx) { D.nx[o] = nx; D.ny[o] = ny; D.nz[o] = nz; }
+            if (D.dist) D.dist[o] = dist;
+            if (D.overlap) D.overlap[o] = ovl_out;
+            if (D.ftx) { D.ftx[o] = ft0; D.fty[o] = ft1; D.ftz[o] = ft2; }
+          } else {
+            st |= RBX_STATUS_SLOT_OVERFLOW;
+          }
+        }
+        ki++;
       }
-      if (D.key) {
-        if (ki < RBX_MAX_KEYS) {
-          const size_t o = (size_t)ki * n_rigid + p;
-          D.key[o] = key;
-          if (D.closest) D.closest[o] = a.pmin >= 0 ? a.gmin : -1;
-          if (D.nx) { D.nx[o] = nx; D.ny[o] = ny; D.nz[o] = nz; }
-          if (D.dist) D.dist[o] = dist;
-          if (D.overlap) D.overlap[o] = ovl_out;
-          if (D.ftx) { D.ftx[o] = ft0; D.fty[o] = ft1; D.ftz[o] = ft2; }
+      // more than kAcc bodies touch this particle: remember what was served
+      // and go over the list again for the rest (slots are then finalized in
+      // ascending dem_id per round, not globally: only the order in which
+      // their forces are added changes)
+      if (overflow) {
+        if (n_served + nk <= 32) {
+          for (int kk = 0; kk < nk; kk++) {
+            int key = 0;
+#pragma unroll
+            for (int j = 0; j < kAcc; j++) if (j == kk) key = keys[j];
+            served[n_served++] = key;
+          }
+          more = true;
         } else {
           st |= RBX_STATUS_SLOT_OVERFLOW;
         }
       }
-      ki++;
-      key = next;
     }
     if (nout < S.ks) S.hist_key_out[(size_t)nout * n_rigid + p] = -1;
     if (D.key)
@@ -388,7 +526,7 @@ k_contact(RbxScene S, RbxCells C, RbxParams P, RbxDiag D, double reach, double h
     S.fx[p] = fx; S.fy[p] = fy; S.fz[p] = fz;
   }
 
-  // ---- 5. chunk partial of SumUpExternalForces :158-175 --------------------
+  // ---- 5. warp partial of SumUpExternalForces :158-175 ---------------------
   double v6[6] = {0, 0, 0, 0, 0, 0};
   if (valid) {
     const double dx = px - S.xcm[3 * body], dy = py - S.xcm[3 * body + 1],
@@ -400,32 +538,16 @@ k_contact(RbxScene S, RbxCells C, RbxParams P, RbxDiag D, double reach, double h
   }
 #pragma unroll
   for (int a = 0; a < 6; a++) v6[a] = rbx_warp_sum(v6[a]);
-  __syncthreads();
   if (lane == 0) {
 #pragma unroll
-    for (int a = 0; a < 6; a++) red[wid][a] = v6[a];
+    for (int a = 0; a < 6; a++) S.chunk_ft[((size_t)chunk * kWarps + wid) * 6 + a] = v6[a];
   }
-  // counters: one atomic per warp into shared, one per CTA into global
-  {
-    unsigned long long g = (unsigned long long)nlist, c = ncand, na = nactive;
+  if (S.counters) {
+    unsigned na = nactive;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      g += __shfl_xor_sync(0xffffffffu, g, o);
-      c += __shfl_xor_sync(0xffffffffu, c, o);
-      na += __shfl_xor_sync(0xffffffffu, na, o);
-    }
-    if (lane == 0) {
-      atomicAdd(&cnt_s[0], g); atomicAdd(&cnt_s[1], na); atomicAdd(&cnt_s[2], c);
-    }
+    for (int o = 16; o > 0; o >>= 1) na += __shfl_xor_sync(0xffffffffu, na, o);
+    if (lane == 0 && na) atomicAdd(&S.counters[1], (unsigned long long)na);
   }
-  __syncthreads();
-  if (tid < 6) {
-    double s = red[0][tid];
-#pragma unroll
-    for (int w2 = 1; w2 < kWarps; w2++) s += red[w2][tid];
-    S.chunk_ft[(size_t)chunk * 6 + tid] = s;
-  }
-  if (tid < 3 && S.counters) atomicAdd(&S.counters[tid], cnt_s[tid]);
 }
 
 }  // namespace
@@ -435,18 +557,21 @@ extern "C" int rbx_contact_mofidi(const RbxScene *scene, const RbxCells *cells,
   if (!scene || !cells || !params) return RBX_ERR_INVALID;
   if (scene->n_chunks <= 0) return RBX_OK;
   if (scene->ks < 1 || (scene->dim != 2 && scene->dim != 3)) return RBX_ERR_INVALID;
-  if (!(params->reach > 0.)) return RBX_ERR_INVALID;
+  if (!(params->reach > 0.) || scene->list_cap < 1) return RBX_ERR_INVALID;
+  if (!scene->nbr_pos || !scene->nbr_dem || !scene->nbr_cnt) return RBX_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream_;
   RbxDiag d;
   if (diag) d = *diag; else memset(&d, 0, sizeof(d));
   const bool uni = params->h_uniform > 0.;
   const int nb = scene->n_chunks;
+  if (uni) k_neighbours<true><<<nb, RBX_CHUNK, 0, st>>>(*scene, *cells, *params, params->reach, params->h_uniform);
+  else k_neighbours<false><<<nb, RBX_CHUNK, 0, st>>>(*scene, *cells, *params, params->reach, 0.);
   if (scene->dim == 3) {
-    if (uni) k_contact<3, true><<<nb, RBX_CHUNK, 0, st>>>(*scene, *cells, *params, d, params->reach, params->h_uniform);
-    else k_contact<3, false><<<nb, RBX_CHUNK, 0, st>>>(*scene, *cells, *params, d, params->reach, 0.);
+    if (uni) k_slots<3, true><<<nb, RBX_CHUNK, 0, st>>>(*scene, *cells, *params, d, params->h_uniform);
+    else k_slots<3, false><<<nb, RBX_CHUNK, 0, st>>>(*scene, *cells, *params, d, 0.);
   } else {
-    if (uni) k_contact<2, true><<<nb, RBX_CHUNK, 0, st>>>(*scene, *cells, *params, d, params->reach, params->h_uniform);
-    else k_contact<2, false><<<nb, RBX_CHUNK, 0, st>>>(*scene, *cells, *params, d, params->reach, 0.);
+    if (uni) k_slots<2, true><<<nb, RBX_CHUNK, 0, st>>>(*scene, *cells, *params, d, params->h_uniform);
+    else k_slots<2, false><<<nb, RBX_CHUNK, 0, st>>>(*scene, *cells, *params, d, 0.);
   }
   RBX_CHECK_LAUNCH();
   return RBX_OK;

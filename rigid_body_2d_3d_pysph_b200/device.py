@@ -54,7 +54,7 @@ class DeviceScene(object):
     def __init__(self, arrays, rigid_names, boundary_names=(), dim=3,
                  kr=1e5, kf=1e3, fric_coeff=0.5, gx=0., gy=0., gz=0.,
                  planar=False, ks=8, radius_scale=3.0, eta_uniform=None,
-                 cap_cells=None, device=None):
+                 cap_cells=None, list_cap=96, device=None):
         if not torch.cuda.is_available():
             raise _lib.RbxError('DeviceScene needs a CUDA device; the '
                                 'rigid-body path has no CPU fallback')
@@ -68,6 +68,7 @@ class DeviceScene(object):
         self.dim = int(dim)
         self.planar = bool(planar)
         self.ks = int(ks)
+        self.list_cap = int(list_cap)
         self.radius_scale = float(radius_scale)
         self.kr, self.kf, self.fric_coeff = float(kr), float(kf), \
             float(fric_coeff)
@@ -176,8 +177,15 @@ class DeviceScene(object):
         self.T = {'chunk_start': self._t(cs, i32),
                   'chunk_body': self._t(cb, i32),
                   'body_chunk': self._t(bc, i32),
-                  'chunk_ft': torch.zeros(max(self.n_chunks, 1) * 6,
+                  'chunk_ft': torch.zeros(max(self.n_chunks, 1) * 24,
                                           dtype=f64, device=dev)}
+        # neighbour lists [list_cap][n_rigid] (scratch of the contact op)
+        nr_ = max(self.n_rigid, 1)
+        self.T['nbr_pos'] = torch.empty(self.list_cap * nr_, dtype=i32,
+                                        device=dev)
+        self.T['nbr_dem'] = torch.empty(self.list_cap * nr_, dtype=i32,
+                                        device=dev)
+        self.T['nbr_cnt'] = torch.zeros(nr_, dtype=i32, device=dev)
         # ---- damping table ---------------------------------------------
         self.eta_mode = 0
         self.T['eta'] = None
@@ -273,8 +281,9 @@ class DeviceScene(object):
             s.is_boundary = _ptr(P['is_boundary'])
             s.normal0 = _ptr(P['normal0'])
             s.normal = _ptr(P['normal'])
+        s.list_cap = self.list_cap
         for n in ['chunk_start', 'chunk_body', 'body_chunk', 'chunk_ft',
-                  'eta', 'eta_row']:
+                  'nbr_pos', 'nbr_dem', 'nbr_cnt', 'eta', 'eta_row']:
             setattr(s, n, _ptr(T[n]))
         for n in ['total_mass', 'izz', 'spacing0', 'xcm', 'vcm', 'ang_mom',
                   'omega', 'force', 'torque', 'R', 'R_prev', 'xcm0', 'vcm0',
