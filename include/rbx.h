@@ -199,6 +199,15 @@ int rbx_contact_mofidi(const RbxScene *scene, const RbxCells *cells,
                        const RbxParams *params, const RbxDiag *diag,
                        void *stream);
 
+/* The two launches of rbx_contact_mofidi, separately (profiling, tests):
+ * neighbours = exact NNPS predicate + source gate (rigid_body_common.py:
+ * 678-679) -> neighbour lists; slots = pair sums, force law, partials.     */
+int rbx_contact_neighbours(const RbxScene *scene, const RbxCells *cells,
+                           const RbxParams *params, void *stream);
+int rbx_contact_slots(const RbxScene *scene, const RbxCells *cells,
+                      const RbxParams *params, const RbxDiag *diag,
+                      void *stream);
+
 /* SumUpExternalForces.reduce (rigid_body_common.py:128-175): chunk partials
  * -> force[3nb], torque[3nb] in a fixed order (deterministic).             */
 int rbx_reduce_bodies(const RbxScene *scene, void *stream);

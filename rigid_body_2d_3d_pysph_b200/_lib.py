@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'csrc', 'librbx.so')
+LIB_PATH = os.environ.get('RBX_LIB') or \
+    os.path.join(_HERE, 'csrc', 'librbx.so')
 
 c_i32, c_i64, c_f64, c_vp = (ctypes.c_int32, ctypes.c_int64, ctypes.c_double,
                               ctypes.c_void_p)
@@ -74,7 +75,8 @@ class RbxDiag(ctypes.Structure):
 # every symbol include/rbx.h declares
 SYMBOLS = ['rbx_version', 'rbx_strerror', 'rbx_sizeof',
            'rbx_cells_workspace_bytes', 'rbx_cells_build', 'rbx_pairs_dump',
-           'rbx_contact_mofidi', 'rbx_reduce_bodies', 'rbx_gtvf_kick',
+           'rbx_contact_mofidi', 'rbx_contact_neighbours',
+           'rbx_contact_slots', 'rbx_reduce_bodies', 'rbx_gtvf_kick',
            'rbx_gtvf_drift', 'rbx_pose_particles', 'rbx_rk2_stage',
            'rbx_gtvf_step']
 
@@ -113,6 +115,10 @@ def load():
                                  c_vp, c_vp, c_vp]
     L.rbx_contact_mofidi.argtypes = [P(RbxScene), P(RbxCells), P(RbxParams),
                                      P(RbxDiag), c_vp]
+    L.rbx_contact_neighbours.argtypes = [P(RbxScene), P(RbxCells),
+                                         P(RbxParams), c_vp]
+    L.rbx_contact_slots.argtypes = [P(RbxScene), P(RbxCells), P(RbxParams),
+                                    P(RbxDiag), c_vp]
     L.rbx_reduce_bodies.argtypes = [P(RbxScene), c_vp]
     L.rbx_gtvf_kick.argtypes = [P(RbxScene), c_f64, c_vp]
     L.rbx_gtvf_drift.argtypes = [P(RbxScene), c_f64, c_vp]

@@ -19,8 +19,10 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines/out: tuning variants (-DRBX_KACC=2 ...) built beside the
+    default library; select one at run time with RBX_LIB=<path>."""
+    if out is None and not force and not needs_build():
         return LIB
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
     cmd = [nvcc, '-O3', '-std=c++17', '-lineinfo',
@@ -29,9 +31,10 @@ def build(force=False, verbose=False):
            '-I', os.path.join(ROOT, 'include'), '-I', HERE]
     if verbose:
         cmd += ['-Xptxas', '-v']
-    cmd += [os.path.join(HERE, s) for s in SOURCES] + ['-o', LIB]
+    cmd += ['-D' + d for d in defines]
+    cmd += [os.path.join(HERE, s) for s in SOURCES] + ['-o', out or LIB]
     subprocess.check_call(cmd)
-    return LIB
+    return out or LIB
 
 
 if __name__ == '__main__':

@@ -42,12 +42,24 @@ struct SlotAcc {
   int gmin;               // its global index (tie rule: lowest index)
 };
 
+#ifndef RBX_KPRE
+#define RBX_KPRE 4
+#endif
+#ifndef RBX_KACC
+#define RBX_KACC 4
+#endif
+#ifndef RBX_NB_MINB
+#define RBX_NB_MINB 6
+#endif
+#ifndef RBX_SLOTS_MINB
+#define RBX_SLOTS_MINB 4
+#endif
 constexpr int kWarps = RBX_CHUNK / 32;
-constexpr int kBatch = 4;   // staged candidates per thread per iteration
-constexpr int kPre = 4;     // list entries in flight per thread in k_slots
+constexpr int kBatch = 4;        // staged candidates per thread per iteration
+constexpr int kPre = RBX_KPRE;   // list entries in flight per thread in k_slots
 
 template <bool UNIFORM_H>
-__global__ void __launch_bounds__(RBX_CHUNK, 6)
+__global__ void __launch_bounds__(RBX_CHUNK, RBX_NB_MINB)
 k_neighbours(RbxScene S, RbxCells C, RbxParams P, double reach, double h_uniform) {
   __shared__ double t_x[RBX_TILE], t_y[RBX_TILE], t_z[RBX_TILE];
   __shared__ double t_h[UNIFORM_H ? 1 : RBX_TILE];
@@ -258,11 +270,11 @@ k_neighbours(RbxScene S, RbxCells C, RbxParams P, double reach, double h_uniform
   }
 }
 
-constexpr int kAcc = 4;     // slots accumulated per pass over the list
+constexpr int kAcc = RBX_KACC;  // slots accumulated per pass over the list
 constexpr int kFields = 10; // ax ay az w1 bx by bz w2 rmin (pmin,gmin)
 
 template <int DIM, bool UNIFORM_H>
-__global__ void __launch_bounds__(RBX_CHUNK, 4)
+__global__ void __launch_bounds__(RBX_CHUNK, RBX_SLOTS_MINB)
 k_slots(RbxScene S, RbxCells C, RbxParams P, RbxDiag D, double h_uniform) {
   // slot accumulators: [slot][field][thread] -> conflict-free, no dynamic
   // register indexing.  Field 9 packs (pmin, gmin) as two ints.
@@ -552,20 +564,39 @@ k_slots(RbxScene S, RbxCells C, RbxParams P, RbxDiag D, double h_uniform) {
 
 }  // namespace
 
-extern "C" int rbx_contact_mofidi(const RbxScene *scene, const RbxCells *cells,
-                                  const RbxParams *params, const RbxDiag *diag, void *stream_) {
+static int check_contact_args(const RbxScene *scene, const RbxCells *cells, const RbxParams *params) {
   if (!scene || !cells || !params) return RBX_ERR_INVALID;
-  if (scene->n_chunks <= 0) return RBX_OK;
   if (scene->ks < 1 || (scene->dim != 2 && scene->dim != 3)) return RBX_ERR_INVALID;
   if (!(params->reach > 0.) || scene->list_cap < 1) return RBX_ERR_INVALID;
   if (!scene->nbr_pos || !scene->nbr_dem || !scene->nbr_cnt) return RBX_ERR_INVALID;
+  return RBX_OK;
+}
+
+extern "C" int rbx_contact_neighbours(const RbxScene *scene, const RbxCells *cells,
+                                      const RbxParams *params, void *stream_) {
+  int rc = check_contact_args(scene, cells, params);
+  if (rc) return rc;
+  if (scene->n_chunks <= 0) return RBX_OK;
+  cudaStream_t st = (cudaStream_t)stream_;
+  const int nb = scene->n_chunks;
+  if (params->h_uniform > 0.)
+    k_neighbours<true><<<nb, RBX_CHUNK, 0, st>>>(*scene, *cells, *params, params->reach, params->h_uniform);
+  else
+    k_neighbours<false><<<nb, RBX_CHUNK, 0, st>>>(*scene, *cells, *params, params->reach, 0.);
+  RBX_CHECK_LAUNCH();
+  return RBX_OK;
+}
+
+extern "C" int rbx_contact_slots(const RbxScene *scene, const RbxCells *cells,
+                                 const RbxParams *params, const RbxDiag *diag, void *stream_) {
+  int rc = check_contact_args(scene, cells, params);
+  if (rc) return rc;
+  if (scene->n_chunks <= 0) return RBX_OK;
   cudaStream_t st = (cudaStream_t)stream_;
   RbxDiag d;
   if (diag) d = *diag; else memset(&d, 0, sizeof(d));
   const bool uni = params->h_uniform > 0.;
   const int nb = scene->n_chunks;
-  if (uni) k_neighbours<true><<<nb, RBX_CHUNK, 0, st>>>(*scene, *cells, *params, params->reach, params->h_uniform);
-  else k_neighbours<false><<<nb, RBX_CHUNK, 0, st>>>(*scene, *cells, *params, params->reach, 0.);
   if (scene->dim == 3) {
     if (uni) k_slots<3, true><<<nb, RBX_CHUNK, 0, st>>>(*scene, *cells, *params, d, params->h_uniform);
     else k_slots<3, false><<<nb, RBX_CHUNK, 0, st>>>(*scene, *cells, *params, d, 0.);
@@ -575,4 +606,11 @@ extern "C" int rbx_contact_mofidi(const RbxScene *scene, const RbxCells *cells,
   }
   RBX_CHECK_LAUNCH();
   return RBX_OK;
+}
+
+extern "C" int rbx_contact_mofidi(const RbxScene *scene, const RbxCells *cells,
+                                  const RbxParams *params, const RbxDiag *diag, void *stream_) {
+  int rc = rbx_contact_neighbours(scene, cells, params, stream_);
+  if (rc) return rc;
+  return rbx_contact_slots(scene, cells, params, diag, stream_);
 }
