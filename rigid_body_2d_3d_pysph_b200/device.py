@@ -161,6 +161,15 @@ class DeviceScene(object):
         sp = []
         for pa in self.rigid:
             nb = int(pa.constants['nb'][0])
+            if 'spacing0' not in pa.constants:
+                # divergence D5: stack_of_cylinders.py:146 passes
+                # `initial_spacing0` but the equations read `spacing0`
+                # (rigid_body_common.py:752, 898); under PySPH the script
+                # cannot run as shipped.  Use the value it meant.
+                if 'initial_spacing0' not in pa.constants:
+                    raise KeyError("array '%s' has no constant spacing0" %
+                                   pa.name)
+                pa.add_constant('spacing0', pa.constants['initial_spacing0'])
             sp.append(np.full(nb, float(pa.constants['spacing0'][0])))
         self.B['spacing0'] = self._t(np.concatenate(sp) if sp
                                      else np.zeros(0), f64)

@@ -47,3 +47,40 @@ def assert_close(got, want, rtol, what, scale=None):
     err = np.max(np.abs(got[ok] - want[ok]))
     assert err <= rtol * scale, '%s: err %.3e > %.1e * %.3e' % (
         what, err, rtol, scale)
+
+
+DENSE_SLOTS = ['contact_force_normal_x', 'contact_force_normal_y',
+               'contact_force_normal_z', 'contact_force_normal_wij',
+               'contact_force_normal_tmp_x', 'contact_force_normal_tmp_y',
+               'contact_force_normal_tmp_z', 'contact_force_dist_tmp',
+               'contact_force_dist', 'overlap', 'ft_x', 'ft_y', 'ft_z',
+               'fn_x', 'fn_y', 'fn_z', 'delta_lt_x', 'delta_lt_y',
+               'delta_lt_z', 'vx_source', 'vy_source', 'vz_source',
+               'x_source', 'y_source', 'z_source', 'ti_x', 'ti_y', 'ti_z',
+               'closest_point_dist_to_source']
+
+
+def load_config(name):
+    """A BASELINE.json config scene frozen by tests/make_config_fixtures.py:
+    (arrays, meta).  Rigid arrays get the reference's dense slot arrays so
+    that the oracle can run them."""
+    arrays, meta = load_scene(os.path.join(GOLDEN, 'cfg_%s.npz' % name))
+    for pa in arrays:
+        if pa.name not in meta['rigid']:
+            continue
+        if 'spacing0' not in pa.constants:      # divergence D5
+            pa.add_constant('spacing0', pa.constants['initial_spacing0'])
+        tnb = int(pa.total_no_bodies[0])
+        for n in DENSE_SLOTS:
+            if n not in pa.properties:
+                pa.add_property(n, stride=tnb)
+        if 'dem_id_source' not in pa.properties:
+            pa.add_property('dem_id_source', type='int', stride=tnb)
+    return arrays, meta
+
+
+def oracle_params(meta, **kw):
+    from oracle import rbo
+    return rbo.make_params(meta['dim'], meta['dt'], meta['kr'], meta['kf'],
+                           meta['fric_coeff'], meta['gx'], meta['gy'],
+                           meta['gz'], **kw)
