@@ -109,7 +109,7 @@ def run_reference(args, rank, world):
     from oracle import rbo
     from rigid_body_2d_3d_pysph_b200.scenes import synthetic_pile
     nb = args.cpu_bodies
-    body, wall, scheme, info = synthetic_pile(nb, seed=0)
+    (body, wall), scheme, info = synthetic_pile(nb, seed=0)
     rbo.add_sparse_history(body, 4)
     p = rbo.make_params(3, DT, KR, KF, MU, 0., -9.81, 0.,
                         eta_uniform=info['eta_uniform'])
@@ -161,6 +161,7 @@ def main():
     ap.add_argument('--cpu-steps', type=int, default=60)
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--ks', type=int, default=8)
+    ap.add_argument('--halo-cap', type=int, default=600000)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
 
@@ -190,17 +191,33 @@ def main():
 
     # ---- scene (one pile per rank: weak scaling) ---------------------------
     t_build = time.perf_counter()
-    body, wall, scheme, info = synthetic_pile(args.bodies, seed=rank)
-    sc = DeviceScene([body, wall], ['body'], ['wall'], dim=3, kr=KR, kf=KF,
-                     fric_coeff=MU, gy=-9.81, ks=args.ks,
+    # N = 1: the whole pile on one GPU.  N > 1: weak scaling, the scene is N
+    # such piles side by side in one walled box, rank k owns x-slab k and
+    # exchanges source-particle halos with its neighbours every step.
+    arrays, scheme, info = synthetic_pile(
+        args.bodies, seed=0, slab=(rank, world),
+        halo_cap=args.halo_cap if world > 1 else 0)
+    body, wall = arrays[0], arrays[1]
+    sc = DeviceScene(arrays, ['body'], [a.name for a in arrays[1:]], dim=3,
+                     kr=KR, kf=KF, fric_coeff=MU, gy=-9.81, ks=args.ks,
                      eta_uniform=info['eta_uniform'], device=dev)
     t_build = time.perf_counter() - t_build
     n_rigid = sc.n_rigid
     n_static_src = info['n_wall_sources']
+    slab = None
+    if world > 1:
+        from rigid_body_2d_3d_pysph_b200.parallel import SlabScene
+        slab = SlabScene(sc, rank, world)
+
+    def run_steps(n):
+        if slab is not None:
+            slab.gtvf_step(DT, n)
+        else:
+            sc.gtvf_step(DT, n, graph=True)
 
     # ---- pre-settle, warm-up -------------------------------------------------
-    sc.gtvf_step(DT, args.settle, graph=True)
-    sc.gtvf_step(DT, args.warmup, graph=True)
+    run_steps(args.settle)
+    run_steps(args.warmup)
     barrier()
     sc.check_status()
     sc.read_counters(reset=True)
@@ -212,12 +229,15 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), \
         torch.cuda.Event(enable_timing=True)
     barrier()
+    halo0 = slab.bytes_recv if slab is not None else 0
     e0.record()
-    sc.gtvf_step(DT, args.steps, graph=True)
+    run_steps(args.steps)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
     sampler.stop_flag = True
+    halo_bytes = (slab.bytes_recv - halo0) / args.steps if slab is not None \
+        else 0
     cnt = sc.read_counters(reset=True)
     sc.check_status()
     if world > 1:
@@ -246,6 +266,8 @@ def main():
         sc.gtvf_drift(DT)
         sc.pose(_lib.POSE_POS | _lib.POSE_VEL | _lib.POSE_VEL_PREV |
                 _lib.POSE_NORMALS)
+        if slab is not None:
+            slab.exchange_halo()
         sc.cells_build()
         ev[0].record()
         sc.contact(DT)
@@ -290,7 +312,10 @@ def main():
         for n in names_in:
             sc.P[n][wall_o:wall_o + wall_n].copy_(host_in[n],
                                                   non_blocking=True)
-        sc._gtvf_step_call(p)
+        if slab is not None:
+            slab.gtvf_step(DT, 1)
+        else:
+            sc._gtvf_step_call(p)
         for n in names_out:
             host_out[n].copy_(sc.B[n], non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
@@ -319,7 +344,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle import rbo
-        cb, cw, _, cinfo = synthetic_pile(args.cpu_bodies, seed=0)
+        (cb, cw), _, cinfo = synthetic_pile(args.cpu_bodies, seed=0)
         rbo.add_sparse_history(cb, 4)
         cp = rbo.make_params(3, DT, KR, KF, MU, 0., -9.81, 0.,
                              eta_uniform=cinfo['eta_uniform'])
@@ -351,11 +376,14 @@ def main():
                     args.bodies, n_rigid, wall_n, args.settle),
                 'bodies_per_gpu': args.bodies,
                 'particles_per_gpu': n_rigid,
-                'parallelism': 'one independent pile per GPU' if world > 1
+                'parallelism': ('%d x-slabs of one scene, bodies owned per '
+                                'slab, source-particle halo exchange (NCCL '
+                                'p2p) every step' % world) if world > 1
                 else 'single GPU',
+                'halo_bytes_per_rank_per_step': halo_bytes,
                 'l2': 'working set (%.1f GB) far larger than the 126 MB L2; '
                 'no flush needed' % (step_b / 1e9),
-                'stepper': 'GTVF', 'ks': args.ks, 'graph': True},
+                'stepper': 'GTVF', 'ks': args.ks, 'graph': world == 1},
             'contact_pairs_per_s': pairs_per_s,
             'contact_pairs_per_step': tot_pairs / args.steps,
             'active_slots_per_step': tot_active / args.steps,

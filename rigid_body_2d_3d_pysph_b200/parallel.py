@@ -1,0 +1,161 @@
+"""Multi-GPU: x-slab decomposition of a large multi-body scene (SURVEY.md
+section 8e), one process per GPU, torch.distributed (NCCL over NVLink on the
+GPU box, gloo in the CPU tests) for the plumbing.
+
+Ownership is by *body*: every rank owns whole bodies (those whose centre of
+mass started in its slab).  All destination work of a body -- contact forces
+on its particles, the force/torque reduction, the integrator -- is therefore
+local, and the "straddler" all-reduce of a particle-wise partition never
+arises.  What crosses ranks each step is the *halo*: the source particles
+(contact_force_is_boundary == 1) of a rank's bodies that lie inside another
+rank's region of interest [x_min - reach, x_max + reach] of its own particles:
+position, velocity, h and dem_id, 64 B per particle, sent after the drift /
+re-pose and before the cell-list build.  Received particles land in the
+'halo' array of the local scene, which is an ordinary static-boundary source
+array to the kernels (scenes.synthetic_pile(halo_cap=...)).
+
+The region of interest is recomputed from the live positions every step, so
+the exchange stays correct even when bodies drift across the initial cuts
+(ownership does not migrate; only the efficiency of the slabs would degrade).
+Static wall particles are replicated per slab when the scene is built.
+
+Per step and rank: one all_gather of 2 doubles (interest interval), one
+all_gather of `world` counts, and point-to-point payload messages only
+between ranks whose intervals overlap (the two slab neighbours).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+HALO_COLS = 8     # x y z u v w h dem_id
+
+
+def interest_interval(x_own, reach):
+    """[x_min - reach, x_max + reach] of the rank's own particles."""
+    if x_own.numel() == 0:
+        return torch.tensor([1e300, -1e300], dtype=torch.float64,
+                            device=x_own.device)
+    return torch.stack([x_own.min() - reach, x_own.max() + reach])
+
+
+def select_halo(cols, intervals, rank):
+    """Rows of `cols` ([n, HALO_COLS], column 0 = x) wanted by each rank.
+
+    intervals: [world, 2] tensor.  Returns a list of row-index tensors, empty
+    for `rank` itself.  Order inside a message = ascending local index, so
+    the exchange is deterministic."""
+    out = []
+    x = cols[:, 0]
+    for q in range(intervals.shape[0]):
+        if q == rank:
+            out.append(torch.zeros(0, dtype=torch.int64, device=cols.device))
+            continue
+        m = (x >= intervals[q, 0]) & (x <= intervals[q, 1])
+        out.append(torch.nonzero(m).flatten())
+    return out
+
+
+def exchange_rows(cols, rows, rank, world, group=None):
+    """Send cols[rows[q]] to rank q, receive what the others send here.
+    Returns the received rows concatenated in rank order ([m, HALO_COLS])."""
+    dev = cols.device
+    counts = torch.tensor([r.numel() for r in rows], dtype=torch.int64,
+                          device=dev)
+    table = [torch.zeros(world, dtype=torch.int64, device=dev)
+             for _ in range(world)]
+    dist.all_gather(table, counts, group=group)
+    table = torch.stack(table).cpu()          # [src, dst] (host sync point)
+    recv_counts = [int(table[q, rank]) for q in range(world)]
+    recv = [torch.empty(recv_counts[q], cols.shape[1], dtype=cols.dtype,
+                        device=dev) for q in range(world)]
+    send = [cols.index_select(0, rows[q]).contiguous() for q in range(world)]
+    ops = []
+    for q in range(world):
+        if q == rank:
+            continue
+        if int(table[rank, q]) > 0:
+            ops.append(dist.P2POp(dist.isend, send[q], q, group))
+        if recv_counts[q] > 0:
+            ops.append(dist.P2POp(dist.irecv, recv[q], q, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    got = torch.cat(recv, 0) if recv else cols[:0]
+    return got, int(counts.sum()), int(sum(recv_counts))
+
+
+class SlabScene(object):
+    """A DeviceScene that is one x-slab of a larger scene."""
+
+    def __init__(self, scene, rank, world, group=None, halo_name='halo'):
+        self.sc = scene
+        self.rank, self.world, self.group = rank, world, group
+        pas = dict((a.name, a) for a in scene.arrays)
+        self.halo_off = scene.p_off[halo_name]
+        self.halo_cap = pas[halo_name].get_number_of_particles()
+        src = scene.T['src_index'].long()
+        self.n_src_static = int((src < self.halo_off).sum().item())
+        # the halo array is the last one and fully flagged
+        assert int(src.numel()) == self.n_src_static + self.halo_cap, \
+            'halo array must be last and fully source-flagged'
+        self.own_src = src[src < scene.n_rigid]
+        self.n_halo = 0
+        self.bytes_sent = 0
+        self.bytes_recv = 0
+        self._set_source_count(0)
+
+    def _set_source_count(self, n_halo):
+        self.n_halo = n_halo
+        self.sc._src.n = self.n_src_static + n_halo
+
+    def exchange_halo(self):
+        sc = self.sc
+        P = sc.P
+        iv = interest_interval(P['x'][:sc.n_rigid], sc.reach)
+        if self.world > 1:
+            ivs = [torch.empty_like(iv) for _ in range(self.world)]
+            dist.all_gather(ivs, iv, group=self.group)
+            ivs = torch.stack(ivs)
+        else:
+            ivs = iv[None, :]
+        idx = self.own_src
+        cols = torch.stack([P['x'][idx], P['y'][idx], P['z'][idx],
+                            P['u'][idx], P['v'][idx], P['w'][idx],
+                            P['h'][idx], P['dem_id'][idx].double()], 1)
+        rows = select_halo(cols, ivs, self.rank)
+        if self.world > 1:
+            got, ns, nr = exchange_rows(cols, rows, self.rank, self.world,
+                                        self.group)
+        else:
+            got, ns, nr = cols[:0], 0, 0
+        if nr > self.halo_cap:
+            raise _lib.RbxError('halo capacity %d < %d received particles' %
+                                (self.halo_cap, nr))
+        o = self.halo_off
+        for c, n in enumerate(['x', 'y', 'z', 'u', 'v', 'w', 'h']):
+            P[n][o:o + nr] = got[:, c]
+        P['dem_id'][o:o + nr] = got[:, 7].to(torch.int32)
+        self._set_source_count(nr)
+        self.bytes_sent += ns * HALO_COLS * 8
+        self.bytes_recv += nr * HALO_COLS * 8
+
+    def gtvf_step(self, dt, nsteps=1):
+        """GTVFIntegrator.one_timestep with the halo exchange between the
+        re-pose (stage 2) and the force evaluation."""
+        sc = self.sc
+        sc.push_touched()
+        for _ in range(nsteps):
+            sc.gtvf_kick(dt)
+            sc.gtvf_drift(dt)
+            sc.pose(_lib.POSE_POS | _lib.POSE_VEL | _lib.POSE_VEL_PREV |
+                    _lib.POSE_NORMALS)
+            self.exchange_halo()
+            sc.cells_build()
+            sc.contact(dt)
+            sc.reduce_bodies()
+            sc.gtvf_kick(dt)
+            sc.pose(_lib.POSE_VEL)
+        sc.steps_done += nsteps
+        sc.mark_device_newer()

@@ -5,7 +5,7 @@ from rigid_body_2d_3d_pysph_b200 import _lib
 from rigid_body_2d_3d_pysph_b200.device import DeviceScene
 from rigid_body_2d_3d_pysph_b200.scenes import synthetic_pile
 nb=int(sys.argv[1]); settle=int(sys.argv[2])
-body, wall, scheme, info = synthetic_pile(nb)
+(body, wall), scheme, info = synthetic_pile(nb)
 sc = DeviceScene([body, wall], ['body'], ['wall'], dim=3, gy=-9.81, eta_uniform=info['eta_uniform'])
 sc.gtvf_step(1e-4, settle, graph=True)
 torch.cuda.synchronize()

@@ -1,0 +1,94 @@
+"""Multi-rank host logic on CPU (gloo, world_size 2): slab scenes number
+bodies consistently, and the halo exchange delivers exactly the foreign
+source particles inside each rank's region of interest."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from rigid_body_2d_3d_pysph_b200.scenes import synthetic_pile
+
+NB = 60        # bodies per slab
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _cols(body):
+    src = np.nonzero(body.contact_force_is_boundary == 1.)[0]
+    c = np.stack([body.x[src], body.y[src], body.z[src], body.u[src],
+                  body.v[src], body.w[src], body.h[src],
+                  body.dem_id[src].astype(np.float64)], 1)
+    return torch.from_numpy(c)
+
+
+def _worker(rank, world, port, q):
+    from rigid_body_2d_3d_pysph_b200 import parallel
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        arrays, _, info = synthetic_pile(NB, slab=(rank, world), halo_cap=4000)
+        body = arrays[0]
+        reach = 3.0 * info['dx']
+        cols = _cols(body)
+        iv = parallel.interest_interval(torch.from_numpy(body.x), reach)
+        ivs = [torch.empty_like(iv) for _ in range(world)]
+        dist.all_gather(ivs, iv)
+        ivs = torch.stack(ivs)
+        rows = parallel.select_halo(cols, ivs, rank)
+        got, ns, nr = parallel.exchange_rows(cols, rows, rank, world)
+        # expectation from the other slab, built locally
+        other, _, _ = synthetic_pile(NB, slab=(1 - rank, world))
+        oc = _cols(other[0]).numpy()
+        lo, hi = float(iv[0]), float(iv[1])
+        want = oc[(oc[:, 0] >= lo) & (oc[:, 0] <= hi)]
+        ok = got.shape[0] == want.shape[0] and \
+            np.array_equal(got.numpy(), want) and nr == want.shape[0]
+        q.put((rank, bool(ok), int(nr), int(ns)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_halo_exchange_gloo_world2():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q))
+             for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] and res[1][1], res
+    # what rank 0 sent is what rank 1 received, and vice versa
+    assert res[0][3] == res[1][2] and res[1][3] == res[0][2]
+    assert res[0][2] > 0 and res[1][2] > 0
+
+
+def test_slab_scenes_tile_the_full_scene():
+    full, _, fi = synthetic_pile(NB, slab=(0, 2), span=2)
+    a0, _, i0 = synthetic_pile(NB, slab=(0, 2))
+    a1, _, i1 = synthetic_pile(NB, slab=(1, 2))
+    assert fi['n_bodies'] == 2 * NB and i0['n_bodies'] == i1['n_bodies'] == NB
+    fb = full[0]
+    for n in ('x', 'y', 'z', 'dem_id', 'is_boundary', 'dx0'):
+        both = np.concatenate([getattr(a0[0], n), getattr(a1[0], n)])
+        assert np.array_equal(getattr(fb, n), both), n
+    assert np.array_equal(np.unique(fb.dem_id), np.arange(2 * NB))
+    assert int(fb.total_no_bodies[0]) == 2 * NB + 1
+    # slab walls cover what the slab's bodies can reach
+    for a in (a0, a1):
+        b, w = a[0], a[1]
+        assert w.x.min() <= b.x.min() - 0.15 and w.x.max() >= b.x.max() + 0.15
