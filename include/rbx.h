@@ -165,10 +165,31 @@ typedef struct {
   double *nx, *ny, *nz, *dist, *overlap, *ftx, *fty, *ftz;
 } RbxDiag;
 
+/* The DEMScheme scene (dem.py): granular (destination) particles first,
+ * boundary particles after.  History entries are the reference's own:
+ * tng_idx = index of the source particle INSIDE ITS ARRAY, tng_dem = its
+ * dem_id, [n_dest * limit], -1 = empty.                                   */
+typedef struct {
+  int32_t n_total, n_dest, n_arrays, limit;
+  double *x, *y, *z, *u, *v, *w, *wx, *wy, *wz;   /* [n_total] */
+  const double *h, *m, *rad_s;                    /* [n_total] */
+  const double *moi;                              /* [n_dest]  */
+  const int32_t *dem_id;                          /* [n_total] */
+  const int32_t *arr_off;    /* [n_total] first global index of its array */
+  const int32_t *arr_start;  /* [n_arrays + 1] array ranges, scheme order */
+  const int32_t *tbl_row;    /* [n_dest] row offset into kn/kt/alpha/mu   */
+  const double *kn, *kt, *alpha, *mu;  /* by row + source dem_id          */
+  double *fx, *fy, *fz, *torx, *tory, *torz;      /* [n_dest] */
+  int32_t *tng_idx, *tng_dem;                     /* [n_dest * limit] */
+  double *tng_x, *tng_y, *tng_z;                  /* [n_dest * limit] */
+  int32_t *total_tng;                             /* [n_dest] */
+  uint32_t *status;
+} RbxDemScene;
+
 int rbx_version(void);
 const char *rbx_strerror(int code);
 /* sizeof(RbxGridInfo, RbxPoints, RbxCells, RbxScene, RbxParams, RbxDiag) for
- * which = 0..5: lets a binding check its struct mirrors. */
+ * which = 0..5, RbxDemScene for 6: lets a binding check its struct mirrors. */
 size_t rbx_sizeof(int which);
 
 /* Scratch bytes needed by rbx_cells_build for a cell list of this capacity. */
@@ -236,6 +257,17 @@ int rbx_pose_particles(const RbxScene *scene, int flags, void *stream);
  * py_stage1 / py_stage2.  Particle update: rbx_pose_particles(POS|VEL).    */
 int rbx_rk2_stage(const RbxScene *scene, int stage, double dt, int fix_q7,
                   void *stream);
+
+/* UpdateTangentialContactsLVCDisplacement.initialize_pair (dem.py:208-293),
+ * BodyForce.initialize, LVCDisplacement.loop (dem.py:35-205) over a cell list
+ * of ALL particles.  torx/tory/torz accumulate across calls, as in the
+ * reference (nothing resets them).                                          */
+int rbx_contact_lvc(const RbxDemScene *scene, const RbxCells *cells,
+                    const RbxParams *params, void *stream);
+
+/* DEMStep.stage1/2/3 (dem.py:595-625); stage in {1, 2, 3}.                  */
+int rbx_dem_step(const RbxDemScene *scene, int stage, double dt,
+                 void *stream);
 
 /* Whole GTVF step [upstream GTVFIntegrator.one_timestep, SURVEY App. C-6]:
  * kick, drift, pose, cells_build, contact, reduce, kick, velocities.

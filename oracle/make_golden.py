@@ -30,6 +30,7 @@ pysph_stub.install()
 import rigid_body_2d  # noqa: E402  (reference module)
 import rigid_body_3d  # noqa: E402  (reference module)
 import rigid_body_common  # noqa: E402  (reference module)
+import dem  # noqa: E402  (reference module)
 from pysph.base.kernels import QuinticSpline  # noqa: E402
 from pysph.base.utils import get_particle_array  # noqa: E402
 from pysph.tools.geometry import get_2d_block, get_3d_block  # noqa: E402
@@ -252,6 +253,78 @@ def run_case(case):
                                        meta['seconds']))
 
 
+DEM_STATE = ['x', 'y', 'z', 'u', 'v', 'w', 'wx', 'wy', 'wz', 'fx', 'fy', 'fz',
+             'torx', 'tory', 'torz', 'tng_idx', 'tng_idx_dem_id', 'tng_x',
+             'tng_y', 'tng_z', 'total_tng_contacts']
+
+
+def run_dem_case():
+    """DEMScheme (dem.py:628-828): LVCDisplacement + tangential-contact
+    bookkeeping + DEMStep under GTVF sequencing.  No script of the reference
+    instantiates the scheme; the constants it needs but does not create
+    (kn, kt, alpha, mu by source dem_id, max_tng_contacts_limit, moi) are
+    added here."""
+    from pysph.base.kernels import CubicSpline
+    rng = np.random.default_rng(3)
+    rad = 0.01
+    nx, ny = 6, 5
+    gx, gy = np.meshgrid(np.arange(nx), np.arange(ny), indexing='ij')
+    x = gx.ravel() * 1.98 * rad + rng.uniform(-0.02, 0.02, nx * ny) * rad
+    y = gy.ravel() * 1.97 * rad + rad * 0.99 + \
+        rng.uniform(-0.02, 0.02, nx * ny) * rad
+    n = x.size
+    m = 2500. * np.pi * rad**2
+    sand = get_particle_array(name='sand', x=x, y=y, h=1.2 * rad, m=m,
+                              rho=2500., rad_s=rad,
+                              u=rng.uniform(-0.05, 0.05, n),
+                              v=rng.uniform(-0.05, 0.05, n))
+    sand.add_property('dem_id', type='int', data=0)
+    sand.add_property('moi', data=0.5 * m * rad**2)
+    # quirk Q13 (dem.py:239-242): initialize_pair indexes the SOURCE array's
+    # dem_id with an index recorded against another array; keep every array
+    # at least as long as the longest one so that read stays in bounds
+    xw = (np.arange(n + 6) - 14) * 2 * rad
+    wall = get_particle_array(name='wall', x=xw, y=np.zeros_like(xw) - rad,
+                              h=1.2 * rad, m=m, rho=2500., rad_s=rad)
+    wall.add_property('dem_id', type='int', data=1)
+    for pa in (sand, wall):
+        for p in ('wx', 'wy', 'wz'):
+            pa.add_property(p)
+    sand.wz[:] = rng.uniform(-5, 5, n)
+    sand.add_constant('max_tng_contacts_limit', 8)
+    sand.add_constant('kn', [1e5, 2e5])
+    sand.add_constant('kt', [2. / 7. * 1e5, 2. / 7. * 2e5])
+    sand.add_constant('alpha', [40., 60.])
+    sand.add_constant('mu', [0.5, 0.3])
+    s = dem.DEMScheme(['sand'], ['wall'], dim=2, gy=-9.81)
+    s.setup_properties([sand, wall])
+    eqs = s.get_equations()
+    st = {'sand': dem.DEMStep()}
+    kernel = CubicSpline(dim=2)
+    arrays = [sand, wall]
+    dt = 2e-5
+    nsteps, save = 60, (1, 2, 5, 10, 30, 60)
+    meta = {'name': 'dem2d', 'granular': ['sand'], 'boundaries': ['wall'],
+            'dim': 2, 'dt': dt, 'gx': 0., 'gy': -9.81, 'gz': 0.,
+            'nsteps': nsteps, 'save_steps': list(save),
+            'radius_scale': kernel.radius_scale}
+    dump(os.path.join(GOLDEN, 'dem2d_scene.npz'), arrays, {'t': 0.0},
+         detailed_output=True, compress=True)
+    out = {}
+    t0 = time.time()
+    for step in range(1, nsteps + 1):
+        interp.gtvf_step(st, eqs, arrays, kernel, (step - 1) * dt, dt)
+        if step in save:
+            for nme in DEM_STATE:
+                out['ref/%d/sand/%s' % (step, nme)] = \
+                    sand.properties[nme].copy()
+    meta['seconds'] = time.time() - t0
+    out['__meta__'] = np.array(json.dumps(meta))
+    np.savez_compressed(os.path.join(GOLDEN, 'dem2d_ref.npz'), **out)
+    print('%-16s %4d steps %6.1fs  contacts %d' % (
+        'dem2d', nsteps, meta['seconds'], sand.total_tng_contacts.sum()))
+
+
 def known_answers():
     """Reference-owned numeric pins."""
     dx = 0.1
@@ -289,9 +362,11 @@ CASES = {
 
 if __name__ == '__main__':
     os.makedirs(GOLDEN, exist_ok=True)
-    which = sys.argv[1:] or list(CASES) + ['known']
+    which = sys.argv[1:] or list(CASES) + ['known', 'dem2d']
     for name in which:
         if name == 'known':
             known_answers()
+        elif name == 'dem2d':
+            run_dem_case()
         else:
             run_case(CASES[name]())

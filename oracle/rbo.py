@@ -201,3 +201,12 @@ def rk2_step(arrays, rigid_names, params, fix_q7=False, ks=0, nsteps=1):
 
 def num_threads():
     return lib().rbo_num_threads()
+
+
+def dem_step(arrays, granular_names, params, nsteps=1):
+    """GTVF step of the DEMScheme path (LVCDisplacement + DEMStep)."""
+    L = lib()
+    arr, keep = pack(arrays, granular_names)
+    for _ in range(nsteps):
+        if L.rbo_dem_step(arr, len(arrays), ctypes.byref(params)):
+            raise RuntimeError('oracle: tangential contact list full')

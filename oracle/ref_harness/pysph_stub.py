@@ -191,6 +191,7 @@ def install():
     builtins.declare = declare     # rigid_body_common.py:130 uses it bare
     pkgs = ['pysph', 'pysph.sph', 'pysph.base', 'pysph.tools', 'pysph.solver',
             'pysph.sph.wc', 'pysph.sph.isph', 'pysph.examples',
+            'pysph.sph.solid_mech',
             'pysph.examples.solid_mech', 'pysph.examples.rigid_body',
             'compyle']
     for p in pkgs:
@@ -223,6 +224,12 @@ def install():
             get_3d_block=geometry.get_3d_block,
             get_2d_tank=geometry.get_2d_tank)
     _module('pysph.solver.solver', Solver=_Solver)
+    # imported (unused) inside DEMScheme._get_gtvf_equations, dem.py:699-705
+    _module('pysph.sph.basic_equations', ContinuityEquation=None,
+            MonaghanArtificialViscosity=None, VelocityGradient3D=None,
+            VelocityGradient2D=None)
+    _module('pysph.sph.solid_mech.basic', IsothermalEOS=None,
+            HookesDeviatoricStressRate=None, MonaghanArtificialStress=None)
     _module('pysph.solver.application', Application=object)
     _module('matplotlib', pyplot=None)
     _module('matplotlib.pyplot')

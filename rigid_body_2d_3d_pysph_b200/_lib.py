@@ -59,6 +59,19 @@ class RbxScene(ctypes.Structure):
                [(n, c_vp) for n in _SCENE_PTRS]
 
 
+_DEM_PTRS = ['x', 'y', 'z', 'u', 'v', 'w', 'wx', 'wy', 'wz', 'h', 'm', 'rad_s',
+             'moi', 'dem_id', 'arr_off', 'arr_start', 'tbl_row', 'kn', 'kt',
+             'alpha', 'mu', 'fx', 'fy', 'fz', 'torx', 'tory', 'torz',
+             'tng_idx', 'tng_dem', 'tng_x', 'tng_y', 'tng_z', 'total_tng',
+             'status']
+
+
+class RbxDemScene(ctypes.Structure):
+    _fields_ = [(n, c_i32) for n in ('n_total', 'n_dest', 'n_arrays',
+                                     'limit')] + \
+               [(n, c_vp) for n in _DEM_PTRS]
+
+
 class RbxParams(ctypes.Structure):
     _fields_ = [('radius_scale', c_f64), ('kr', c_f64), ('kf', c_f64),
                 ('fric_coeff', c_f64), ('gx', c_f64), ('gy', c_f64),
@@ -78,7 +91,7 @@ SYMBOLS = ['rbx_version', 'rbx_strerror', 'rbx_sizeof',
            'rbx_contact_mofidi', 'rbx_contact_neighbours',
            'rbx_contact_slots', 'rbx_reduce_bodies', 'rbx_gtvf_kick',
            'rbx_gtvf_drift', 'rbx_pose_particles', 'rbx_rk2_stage',
-           'rbx_gtvf_step']
+           'rbx_gtvf_step', 'rbx_contact_lvc', 'rbx_dem_step']
 
 _lib = None
 
@@ -128,8 +141,11 @@ def load():
     L.rbx_gtvf_step.argtypes = [P(RbxScene), P(RbxPoints), P(RbxCells),
                                 P(RbxParams), c_vp, ctypes.c_size_t,
                                 ctypes.c_int, c_vp]
+    L.rbx_contact_lvc.argtypes = [P(RbxDemScene), P(RbxCells), P(RbxParams),
+                                  c_vp]
+    L.rbx_dem_step.argtypes = [P(RbxDemScene), ctypes.c_int, c_f64, c_vp]
     for i, cls in enumerate([RbxGridInfo, RbxPoints, RbxCells, RbxScene,
-                             RbxParams, RbxDiag]):
+                             RbxParams, RbxDiag, RbxDemScene]):
         if L.rbx_sizeof(i) != ctypes.sizeof(cls):
             raise RbxError('ABI mismatch for %s: library %d bytes, binding %d'
                            % (cls.__name__, L.rbx_sizeof(i),

@@ -61,17 +61,59 @@ class StepPlan(object):
         self.sequencing = 'gtvf'
 
 
+_KNOWN_DEM = ('UpdateTangentialContactsLVCDisplacement', 'BodyForce',
+              'LVCDisplacement')
+
+
+def _plan_dem(seen, integrator, plan):
+    """DEMScheme's equation list (dem.py:697-756)."""
+    for need in _KNOWN_DEM:
+        if need not in seen:
+            raise NotImplementedError('DEM path needs %s' % need)
+    plan.kind = 'dem'
+    plan.rigid = [eq.dest for eq in seen['LVCDisplacement']]
+    src = []
+    for eq in seen['LVCDisplacement']:
+        for s in (eq.sources or []):
+            if s not in src:
+                src.append(s)
+    plan.boundaries = [s for s in src if s not in plan.rigid]
+    bf = seen['BodyForce'][0]
+    plan.gx, plan.gy, plan.gz = bf.gx, bf.gy, bf.gz
+    for name in plan.rigid:
+        st = integrator.steppers.get(name)
+        if st is None or st.kind != 'dem':
+            raise NotImplementedError('array %s needs a DEMStep' % name)
+    if integrator.sequencing != 'gtvf':
+        raise NotImplementedError('DEMStep runs under GTVF sequencing')
+    return plan
+
+
 def plan_from_equations(equations, integrator):
-    """Validate the equation list against the one program the device runs
-    (rigid_body_3d.py:641-698) and extract its parameters."""
+    """Validate the equation list against the programs the device runs
+    (rigid_body_3d.py:641-698, dem.py:697-756) and extract the parameters."""
     from .equation import MultiStageEquations
     plan = StepPlan()
+    plan.kind = 'rigid'
     if isinstance(equations, MultiStageEquations):
         groups = []
         for stage in equations.groups:
             groups.extend(stage)
     else:
         groups = list(equations)
+    names = set(eq.__class__.__name__ for g in groups for eq in g.equations)
+    if 'LVCDisplacement' in names or \
+            'UpdateTangentialContactsLVCDisplacement' in names:
+        seen = {}
+        for g in groups:
+            for eq in g.equations:
+                name = eq.__class__.__name__
+                if name not in _KNOWN_DEM:
+                    raise NotImplementedError(
+                        'equation %s has no CUDA implementation on the DEM '
+                        'path' % name)
+                seen.setdefault(name, []).append(eq)
+        return _plan_dem(seen, integrator, plan)
     seen = {}
     for g in groups:
         for eq in g.equations:

@@ -72,6 +72,14 @@ class Solver(object):
         self.particles = particles
         plan = plan_from_equations(equations, self.integrator)
         radius_scale = getattr(self.kernel, 'radius_scale', 3.0)
+        self.plan = plan
+        if plan.kind == 'dem':
+            from ..dem import DemDeviceScene
+            self.scene = DemDeviceScene(
+                particles, plan.rigid, plan.boundaries, dim=self.dim,
+                gx=plan.gx, gy=plan.gy, gz=plan.gz, radius_scale=radius_scale)
+            self.integrator.set_scene(self.scene)
+            return
         self.scene = DeviceScene(
             particles, plan.rigid, plan.boundaries, dim=self.dim, kr=plan.kr,
             kf=plan.kf, fric_coeff=plan.fric_coeff, gx=plan.gx, gy=plan.gy,

@@ -302,6 +302,7 @@ extern "C" size_t rbx_sizeof(int which) {
     case 3: return sizeof(RbxScene);
     case 4: return sizeof(RbxParams);
     case 5: return sizeof(RbxDiag);
+    case 6: return sizeof(RbxDemScene);
     default: return 0;
   }
 }
