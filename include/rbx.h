@@ -124,6 +124,7 @@ typedef struct {
    * Written and read inside rbx_contact_mofidi (scratch between its two
    * launches). */
   int32_t *nbr_pos, *nbr_dem, *nbr_cnt;
+  int32_t *chunk_perm;        /* reserved (unused)                       */
   /* per body */
   const double *total_mass, *izz, *spacing0; /* [n_bodies]               */
   double *xcm, *vcm, *ang_mom, *omega;       /* [3 n_bodies]             */

@@ -43,7 +43,7 @@ struct SlotAcc {
 };
 
 #ifndef RBX_KPRE
-#define RBX_KPRE 4
+#define RBX_KPRE 2
 #endif
 #ifndef RBX_KACC
 #define RBX_KACC 4
@@ -307,6 +307,7 @@ k_slots(RbxScene S, RbxCells C, RbxParams P, RbxDiag D, double h_uniform) {
     unsigned st = 0u;
     const double hij_u = 0.5 * (ph + h_uniform);
     const double rmin0 = 4. * spacing0;              // :765
+    const double vol = md / rhod;
 
     int nout = 0, ki = 0;
     // A particle touching more than kAcc bodies takes further rounds; the
@@ -323,28 +324,55 @@ k_slots(RbxScene S, RbxCells C, RbxParams P, RbxDiag D, double h_uniform) {
       for (int k = 0; k < kAcc; k++) keys[k] = 0x7fffffff;
       int nk = 0;
       bool overflow = false;       // some key did not fit this round
+      // software pipeline over the list, kPre entries per stage:
+      //   stage L: list loads (dem, pos)        for batch b + 2
+      //   stage G: position gathers             for batch b + 1
+      //   stage C: pair math + accumulation     for batch b
+      // so that the two dependent memory round trips (list -> gather) of
+      // later batches overlap the FP64 chain of the current one.
+      int ddL[kPre], qqL[kPre];            // loaded lists, batch b + 1 / b + 2
+      int ddG[kPre], qqG[kPre];            // batch whose gathers are in flight
+      double gx[kPre], gy[kPre], gz[kPre], gh[kPre];
+      auto load_lists = [&](int e0, int *dd_, int *qq_) {
+#pragma unroll
+        for (int k = 0; k < kPre; k++) {
+          const int e = e0 + k;
+          const bool in = e < nlist;
+          dd_[k] = in ? ldem[(size_t)e * n_rigid] : -1;
+          qq_[k] = in ? lpos[(size_t)e * n_rigid] : 0;
+        }
+        if (n_served) {
+#pragma unroll
+          for (int k = 0; k < kPre; k++)
+            for (int j = 0; j < n_served; j++) if (served[j] == dd_[k]) dd_[k] = -1;
+        }
+      };
+      load_lists(0, ddG, qqG);
+#pragma unroll
+      for (int k = 0; k < kPre; k++) {
+        if (ddG[k] >= 0) {
+          gx[k] = C.sx[qqG[k]]; gy[k] = C.sy[qqG[k]]; gz[k] = C.sz[qqG[k]];
+          if (!UNIFORM_H) gh[k] = C.sh[qqG[k]];
+        }
+      }
+      load_lists(kPre, ddL, qqL);
       for (int e0 = 0; e0 < nlist; e0 += kPre) {
         int dd[kPre], qq[kPre];
         double sx[kPre], sy[kPre], sz[kPre], sh[kPre];
 #pragma unroll
         for (int k = 0; k < kPre; k++) {
-          const int e = e0 + k;
-          const bool in = e < nlist;
-          dd[k] = in ? ldem[(size_t)e * n_rigid] : -1;
-          qq[k] = in ? lpos[(size_t)e * n_rigid] : 0;
-        }
-        if (n_served) {
-#pragma unroll
-          for (int k = 0; k < kPre; k++)
-            for (int j = 0; j < n_served; j++) if (served[j] == dd[k]) dd[k] = -1;
+          dd[k] = ddG[k]; qq[k] = qqG[k];
+          sx[k] = gx[k]; sy[k] = gy[k]; sz[k] = gz[k]; sh[k] = gh[k];
+          ddG[k] = ddL[k]; qqG[k] = qqL[k];
         }
 #pragma unroll
-        for (int k = 0; k < kPre; k++) {
-          if (dd[k] >= 0) {
-            sx[k] = C.sx[qq[k]]; sy[k] = C.sy[qq[k]]; sz[k] = C.sz[qq[k]];
-            if (!UNIFORM_H) sh[k] = C.sh[qq[k]];
+        for (int k = 0; k < kPre; k++) {       // stage G for batch b + 1
+          if (ddG[k] >= 0) {
+            gx[k] = C.sx[qqG[k]]; gy[k] = C.sy[qqG[k]]; gz[k] = C.sz[qqG[k]];
+            if (!UNIFORM_H) gh[k] = C.sh[qqG[k]];
           }
         }
+        load_lists(e0 + 2 * kPre, ddL, qqL);   // stage L for batch b + 2
 #pragma unroll
         for (int k = 0; k < kPre; k++) {
           const int d = dd[k];
@@ -361,7 +389,7 @@ k_slots(RbxScene S, RbxCells C, RbxParams P, RbxDiag D, double h_uniform) {
               nk++;
 #pragma unroll
               for (int f = 0; f < 8; f++) acc[sl][f][tid] = 0.;
-              acc[sl][8][tid] = rmin0;
+              acc[sl][8][tid] = rmin0 * rmin0;   // r2 threshold for "closer"
               reinterpret_cast<int2 *>(&acc[sl][9][tid])[0] = make_int2(-1, 0x7fffffff);
             } else {
               overflow = true;
@@ -369,26 +397,40 @@ k_slots(RbxScene S, RbxCells C, RbxParams P, RbxDiag D, double h_uniform) {
             }
           }
           const double x0 = px - sx[k], x1 = py - sy[k], x2 = pz - sz[k];
-          const double rij = sqrt(rbx_r2(x0, x1, x2));
+          // 1/r from rsqrt (1 ulp) instead of sqrt + division: the sums
+          // below move by a few ulp (tolerance 1e-10), the dependent FP64
+          // chain per entry is 3x shorter.  The closest-point decision, which
+          // must match the CPU path bit for bit, still compares correctly
+          // rounded sqrt values (below).
+          const double r2 = rbx_r2(x0, x1, x2);
+          const double rinv = rsqrt(r2);
+          const double rij = r2 * rinv;
           const double hij = UNIFORM_H ? hij_u : 0.5 * (ph + sh[k]);
           const double wij = rbx_quintic<DIM>(rij, hij);
-          const double tmp1 = md / (rhod * rij) * wij;   // :683
-          const double tmp2 = md / (rhod) * wij;         // :803
+          const double tmp2 = vol * wij;                 // :803  m/rho * W
+          const double tmp1 = tmp2 * rinv;               // :683  m/(rho r) * W
           acc[sl][0][tid] += x0 * tmp1;                  // :686-688
           acc[sl][1][tid] += x1 * tmp1;
           acc[sl][2][tid] += x2 * tmp1;
-          acc[sl][3][tid] += tmp1 * rij;                 // :690
+          acc[sl][3][tid] += tmp2;                       // :690  tmp1 * r
           acc[sl][4][tid] += x0 * tmp2;                  // :807 (n . sum)
           acc[sl][5][tid] += x1 * tmp2;
           acc[sl][6][tid] += x2 * tmp2;
-          acc[sl][7][tid] += tmp2;                       // :809
-          const double rmin = acc[sl][8][tid];
-          if (rij <= rmin) {                             // :811 (+ tie rule Q6)
+          // :809: the second weight sum equals the first (tmp1*r == tmp2)
+          const double r2min = acc[sl][8][tid];
+          if (r2 <= r2min * (1. + 1e-14)) {              // :811 (+ tie rule Q6)
+            // possible new closest source: decide exactly as the reference
+            // does, on correctly rounded distances
             const int2 pg = reinterpret_cast<int2 *>(&acc[sl][9][tid])[0];
-            const int g = C.gidx[qq[k]];
-            if (rij < rmin || (pg.x >= 0 && g < pg.y)) {
-              acc[sl][8][tid] = rij;
-              reinterpret_cast<int2 *>(&acc[sl][9][tid])[0] = make_int2(qq[k], g);
+            const double rex = sqrt(r2);
+            const double rmin = (pg.x >= 0) ? sqrt(acc[sl][7][tid]) : rmin0;
+            bool take = rex < rmin;
+            if (!take && pg.x >= 0 && rex == rmin)     // exact tie: lowest
+              take = C.gidx[qq[k]] < C.gidx[pg.x];     // global index wins
+            if (take) {
+              acc[sl][7][tid] = r2;                      // exact r2 of the best
+              acc[sl][8][tid] = r2;
+              reinterpret_cast<int2 *>(&acc[sl][9][tid])[0] = make_int2(qq[k], 0);
             }
           }
         }
@@ -413,7 +455,7 @@ k_slots(RbxScene S, RbxCells C, RbxParams P, RbxDiag D, double h_uniform) {
         const double a_ax = acc[sl][0][tid], a_ay = acc[sl][1][tid], a_az = acc[sl][2][tid];
         const double a_w1 = acc[sl][3][tid];
         const double a_bx = acc[sl][4][tid], a_by = acc[sl][5][tid], a_bz = acc[sl][6][tid];
-        const double a_w2 = acc[sl][7][tid];
+        const double a_w2 = a_w1;
         const int2 pg = reinterpret_cast<int2 *>(&acc[sl][9][tid])[0];
         // ComputeContactForceNormals.post_loop :705-723
         double nx = 0., ny = 0., nz = 0.;
@@ -427,7 +469,8 @@ k_slots(RbxScene S, RbxCells C, RbxParams P, RbxDiag D, double h_uniform) {
         double dist = 0.;
         if (a_w2 > 1e-12) dist = (nx * a_bx + ny * a_by + nz * a_bz) / a_w2;
         double vxs = 0., vys = 0., vzs = 0.;
-        if (pg.x >= 0) { vxs = S.u[pg.y]; vys = S.v[pg.y]; vzs = S.w[pg.y]; }
+        const int gmin = pg.x >= 0 ? C.gidx[pg.x] : -1;
+        if (pg.x >= 0) { vxs = S.u[gmin]; vys = S.v[gmin]; vzs = S.w[gmin]; }
 
         // previous state of this slot
         double dl0 = 0., dl1 = 0., dl2 = 0., fn0 = 0., fn1 = 0., fn2 = 0.;
@@ -502,7 +545,7 @@ k_slots(RbxScene S, RbxCells C, RbxParams P, RbxDiag D, double h_uniform) {
           if (ki < RBX_MAX_KEYS) {
             const size_t o = (size_t)ki * n_rigid + p;
             D.key[o] = key;
-            if (D.closest) D.closest[o] = pg.x >= 0 ? pg.y : -1;
+            if (D.closest) D.closest[o] = gmin;
             if (D.nx) { D.nx[o] = nx; D.ny[o] = ny; D.nz[o] = nz; }
             if (D.dist) D.dist[o] = dist;
             if (D.overlap) D.overlap[o] = ovl_out;

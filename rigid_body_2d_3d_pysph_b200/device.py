@@ -195,6 +195,7 @@ class DeviceScene(object):
         self.T['nbr_dem'] = torch.empty(self.list_cap * nr_, dtype=i32,
                                         device=dev)
         self.T['nbr_cnt'] = torch.zeros(nr_, dtype=i32, device=dev)
+        self.T['chunk_perm'] = torch.zeros(nr_, dtype=i32, device=dev)
         # ---- damping table ---------------------------------------------
         self.eta_mode = 0
         self.T['eta'] = None
@@ -292,7 +293,8 @@ class DeviceScene(object):
             s.normal = _ptr(P['normal'])
         s.list_cap = self.list_cap
         for n in ['chunk_start', 'chunk_body', 'body_chunk', 'chunk_ft',
-                  'nbr_pos', 'nbr_dem', 'nbr_cnt', 'eta', 'eta_row']:
+                  'nbr_pos', 'nbr_dem', 'nbr_cnt', 'chunk_perm', 'eta',
+                  'eta_row']:
             setattr(s, n, _ptr(T[n]))
         for n in ['total_mass', 'izz', 'spacing0', 'xcm', 'vcm', 'ang_mom',
                   'omega', 'force', 'torque', 'R', 'R_prev', 'xcm0', 'vcm0',
