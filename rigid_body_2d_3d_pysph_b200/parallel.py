@@ -120,13 +120,33 @@ class SlabScene(object):
             ivs = torch.stack(ivs)
         else:
             ivs = iv[None, :]
+        ivh = ivs.cpu()                      # host sync 1 (2 doubles / rank)
+        # my sources lie inside my own interval shrunk by the reach; only
+        # ranks whose interval overlaps that can want any of them (the two
+        # slab neighbours unless bodies have wandered)
+        lo_own = float(ivh[self.rank, 0]) + sc.reach
+        hi_own = float(ivh[self.rank, 1]) - sc.reach
         idx = self.own_src
-        cols = torch.stack([P['x'][idx], P['y'][idx], P['z'][idx],
-                            P['u'][idx], P['v'][idx], P['w'][idx],
-                            P['h'][idx], P['dem_id'][idx].double()], 1)
-        rows = select_halo(cols, ivs, self.rank)
+        xs = P['x'][idx]
+        rows = []
+        empty = torch.zeros(0, dtype=torch.int64, device=xs.device)
+        for q in range(self.world):
+            lo_q, hi_q = float(ivh[q, 0]), float(ivh[q, 1])
+            if q == self.rank or hi_q < lo_own or lo_q > hi_own:
+                rows.append(empty)
+                continue
+            rows.append(torch.nonzero((xs >= lo_q) & (xs <= hi_q)).flatten())
+        sel = torch.cat(rows)
+        gsel = idx[sel]
+        cols = torch.stack([P['x'][gsel], P['y'][gsel], P['z'][gsel],
+                            P['u'][gsel], P['v'][gsel], P['w'][gsel],
+                            P['h'][gsel], P['dem_id'][gsel].double()], 1)
+        # rows of `cols` per destination are consecutive blocks
+        offs = np.cumsum([0] + [r.numel() for r in rows])
+        rel = [torch.arange(int(offs[q]), int(offs[q + 1]), device=xs.device)
+               for q in range(self.world)]
         if self.world > 1:
-            got, ns, nr = exchange_rows(cols, rows, self.rank, self.world,
+            got, ns, nr = exchange_rows(cols, rel, self.rank, self.world,
                                         self.group)
         else:
             got, ns, nr = cols[:0], 0, 0
