@@ -282,9 +282,24 @@ def main():
     step_b, contact_b = algorithmic_bytes(n_rigid, n_static_src,
                                           active_per_step, sc.n_bodies)
     peak, peak_src = peaks()
-    roof = {'bound': 'hbm', 'kernel': 'k_contact (rbx_contact_mofidi)',
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')) as f:
+            tr = json.load(f)
+        if tr['config']['bodies'] == args.bodies:
+            traffic = tr['contact_dram_bytes_per_evaluation']
+    except Exception:
+        pass
+    roof = {'bound': 'hbm',
+            'kernel': 'contact evaluation = k_neighbours + k_slots '
+            '(rbx_contact_mofidi; k_slots is the longer of the two)',
             'achieved': contact_b / (contact_ms * 1e-3) / 1e9, 'peak': peak,
-            'unit': 'GB/s', 'peak_source': peak_src, 'traffic': None,
+            'unit': 'GB/s', 'peak_source': peak_src, 'traffic': traffic,
+            'traffic_source': 'profiles/r01_traffic.json (ncu dram__bytes '
+            'read+write of both launches)' if traffic else None,
+            'secondary_limiter': 'FP64 pipe / issue (k_neighbours 43 % FP64, '
+            '70 % issue active) and latency (k_slots 24 % FP64, 43 % issue '
+            'active): see profiles/',
             'ms_per_launch': contact_ms,
             'algorithmic_bytes_per_launch': contact_b}
     roof['frac'] = roof['achieved'] / peak
@@ -361,8 +376,9 @@ def main():
                    min(args.settle, args.cpu_settle), args.cpu_steps)}
 
     if rank == 0:
-        launches_per_step = 13   # bodies, pose, 8 cell-list kernels, contact,
-        #                          bodies, pose (memsets not counted)
+        launches_per_step = 14   # bodies, pose, 8 cell-list kernels,
+        #                          k_neighbours, k_slots, bodies, pose
+        #                          (memsets not counted)
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT,
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
