@@ -86,6 +86,9 @@ typedef struct {
   int32_t *gidx;       /* [cap_points] sorted -> global particle index   */
   double *sx, *sy, *sz, *sh; /* [cap_points] sorted copies              */
   int32_t *sdem;       /* [cap_points] */
+  const uint32_t *cond; /* device word or NULL: when it reads 0 the build is
+                           skipped (neighbour lists still valid, see
+                           RbxScene.rebuild)                              */
 } RbxCells;
 
 /* The scene: global SoA over all particles (rigid-body particles first,
@@ -119,10 +122,12 @@ typedef struct {
   const int32_t *body_chunk;  /* [n_bodies + 1] chunk ranges per body    */
   double *chunk_ft;           /* [n_chunks * 4 * 6] per-warp partial
                                  force, torque                           */
-  /* in-range gated neighbours, [list_cap][n_rigid]: sorted position in the
-   * cell list and source dem_id; nbr_cnt[n_rigid] entries per particle.
-   * Written and read inside rbx_contact_mofidi (scratch between its two
-   * launches). */
+  /* Neighbour lists, [list_cap][n_rigid]: global index and dem_id of every
+   * gated source within reach + skin of the particle when the list was
+   * built; nbr_cnt[n_rigid] entries per particle.  Built by
+   * rbx_contact_neighbours when *rebuild != 0, reused otherwise;
+   * rbx_contact_slots applies the exact neighbour predicate to every entry
+   * with the current positions, so the pair set is independent of the skin. */
   int32_t *nbr_pos, *nbr_dem, *nbr_cnt;
   int32_t *chunk_perm;        /* reserved (unused)                       */
   /* per body */
@@ -146,6 +151,13 @@ typedef struct {
    * (in-contact) slots, [2] candidate distance tests                     */
   uint32_t *status;
   unsigned long long *counters;
+  /* list reuse: rebuild[0] != 0 <=> lists must be rebuilt this evaluation.
+   * Set by the drift / RK2 kernels when a body has moved more than skin/2
+   * since the last build (|xcm - xcm_ref| + |R - R_ref|_F * rmax), by the
+   * host after it changed positions; cleared after a rebuild.             */
+  uint32_t *rebuild;
+  double *xcm_ref, *R_ref;    /* [3 n_bodies], [9 n_bodies] at last build */
+  const double *rmax;         /* [n_bodies] max |body-frame position|     */
 } RbxScene;
 
 typedef struct {
@@ -155,6 +167,8 @@ typedef struct {
   double dt;
   double reach;     /* radius_scale * h_max over ALL arrays = minimum cell edge */
   double h_uniform; /* > 0: every particle has this h (skips the h loads)  */
+  double skin;      /* >= 0: extra radius of the neighbour lists; 0 rebuilds
+                       them at every evaluation                            */
 } RbxParams;
 
 /* Optional per-slot diagnostics of one contact evaluation, slot-major
@@ -241,8 +255,11 @@ int rbx_gtvf_kick(const RbxScene *scene, double dt, void *stream);
 
 /* GTVFRigidBody{3D,2D}Step.py_stage2 + normalize_R_orientation
  * (rigid_body_3d.py:97-132, rigid_body_common.py:178-203): drift of xcm, R
- * (R_prev keeps the pre-drift orientation), inertia update.                */
-int rbx_gtvf_drift(const RbxScene *scene, double dt, void *stream);
+ * (R_prev keeps the pre-drift orientation), inertia update.  Also raises
+ * RbxScene.rebuild when a body has moved more than skin/2 since the
+ * neighbour lists were built.                                              */
+int rbx_gtvf_drift(const RbxScene *scene, double dt, double skin,
+                   void *stream);
 
 /* stage1/stage3 (velocities, rigid_body_3d.py:62-95, 192-225) and stage2
  * (positions + boundary normals, :134-169) of the body particles.
@@ -257,7 +274,7 @@ int rbx_pose_particles(const RbxScene *scene, int flags, void *stream);
  * (fix_q7 != 0 saves ang_mom0 of every body), 1 and 2 =
  * py_stage1 / py_stage2.  Particle update: rbx_pose_particles(POS|VEL).    */
 int rbx_rk2_stage(const RbxScene *scene, int stage, double dt, int fix_q7,
-                  void *stream);
+                  double skin, void *stream);
 
 /* UpdateTangentialContactsLVCDisplacement.initialize_pair (dem.py:208-293),
  * BodyForce.initialize, LVCDisplacement.loop (dem.py:35-205) over a cell list

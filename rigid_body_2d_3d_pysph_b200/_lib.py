@@ -39,7 +39,7 @@ class RbxCells(ctypes.Structure):
     _fields_ = [('cap_cells', c_i32), ('cap_points', c_i32), ('info', c_vp),
                 ('cell_start', c_vp), ('cell_of', c_vp), ('rank', c_vp),
                 ('gidx', c_vp), ('sx', c_vp), ('sy', c_vp), ('sz', c_vp),
-                ('sh', c_vp), ('sdem', c_vp)]
+                ('sh', c_vp), ('sdem', c_vp), ('cond', c_vp)]
 
 
 _SCENE_INTS = ['n_total', 'n_rigid', 'n_bodies', 'n_chunks', 'dim', 'ks',
@@ -52,7 +52,8 @@ _SCENE_PTRS = ['x', 'y', 'z', 'u', 'v', 'w', 'h', 'm', 'rho', 'dem_id',
                'ang_mom', 'omega', 'force', 'torque', 'R', 'R_prev', 'iinv_b',
                'iinv_g', 'xcm0', 'vcm0', 'ang_mom0', 'R0', 'eta', 'eta_row',
                'hist_key_in', 'hist_dlt_in', 'hist_fn_in', 'hist_key_out',
-               'hist_dlt_out', 'hist_fn_out', 'status', 'counters']
+               'hist_dlt_out', 'hist_fn_out', 'status', 'counters', 'rebuild',
+               'xcm_ref', 'R_ref', 'rmax']
 
 
 class RbxScene(ctypes.Structure):
@@ -77,7 +78,7 @@ class RbxParams(ctypes.Structure):
     _fields_ = [('radius_scale', c_f64), ('kr', c_f64), ('kf', c_f64),
                 ('fric_coeff', c_f64), ('gx', c_f64), ('gy', c_f64),
                 ('gz', c_f64), ('dt', c_f64), ('reach', c_f64),
-                ('h_uniform', c_f64)]
+                ('h_uniform', c_f64), ('skin', c_f64)]
 
 
 class RbxDiag(ctypes.Structure):
@@ -135,10 +136,10 @@ def load():
                                     P(RbxDiag), c_vp]
     L.rbx_reduce_bodies.argtypes = [P(RbxScene), c_vp]
     L.rbx_gtvf_kick.argtypes = [P(RbxScene), c_f64, c_vp]
-    L.rbx_gtvf_drift.argtypes = [P(RbxScene), c_f64, c_vp]
+    L.rbx_gtvf_drift.argtypes = [P(RbxScene), c_f64, c_f64, c_vp]
     L.rbx_pose_particles.argtypes = [P(RbxScene), ctypes.c_int, c_vp]
     L.rbx_rk2_stage.argtypes = [P(RbxScene), ctypes.c_int, c_f64,
-                                ctypes.c_int, c_vp]
+                                ctypes.c_int, c_f64, c_vp]
     L.rbx_gtvf_step.argtypes = [P(RbxScene), P(RbxPoints), P(RbxCells),
                                 P(RbxParams), c_vp, ctypes.c_size_t,
                                 ctypes.c_int, c_vp]

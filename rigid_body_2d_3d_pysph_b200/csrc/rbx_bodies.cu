@@ -95,6 +95,20 @@ __device__ __forceinline__ void kick_body(const RbxScene &S, int b, double dtb2)
   }
 }
 
+// Has body b moved more than skin/2 since the neighbour lists were built?
+// |x_p - x_p,ref| = |dxcm + (R - R_ref) r0| <= |dxcm| + |R - R_ref|_F rmax.
+__device__ __forceinline__ void check_displacement(const RbxScene &S, int b, double skin) {
+  if (!S.rebuild || !S.xcm_ref) return;
+  const int i3 = 3 * b, i9 = 9 * b;
+  double d2 = 0., r2 = 0.;
+#pragma unroll
+  for (int j = 0; j < 3; j++) { const double d = S.xcm[i3 + j] - S.xcm_ref[i3 + j]; d2 += d * d; }
+#pragma unroll
+  for (int k = 0; k < 9; k++) { const double d = S.R[i9 + k] - S.R_ref[i9 + k]; r2 += d * d; }
+  const double bound = sqrt(d2) + sqrt(r2) * S.rmax[b];
+  if (!(bound <= 0.5 * skin)) atomicOr(S.rebuild, 1u);   // NaN also rebuilds
+}
+
 __device__ __forceinline__ void drift_body(const RbxScene &S, int b, double dt) {
   const int i3 = 3 * b, i9 = 9 * b;
   const int nd = S.planar ? 2 : 3;
@@ -109,7 +123,7 @@ __device__ __forceinline__ void drift_body(const RbxScene &S, int b, double dt) 
 
 // mode bits: 1 = reduce chunk partials, 2 = kick, 4 = drift, 8 = kick before drift
 // order executed: [reduce] [kick (post)] [kick (pre)] [drift]
-__global__ void k_bodies(RbxScene S, int mode, double dt) {
+__global__ void k_bodies(RbxScene S, int mode, double dt, double skin) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= S.n_bodies) return;
@@ -132,10 +146,10 @@ __global__ void k_bodies(RbxScene S, int mode, double dt) {
   if (lane != 0) return;
   if (mode & 2) kick_body(S, b, dt / 2.);
   if (mode & 8) kick_body(S, b, dt / 2.);
-  if (mode & 4) drift_body(S, b, dt);
+  if (mode & 4) { drift_body(S, b, dt); check_displacement(S, b, skin); }
 }
 
-__global__ void k_rk2(RbxScene S, int stage, double dt, int fix_q7) {
+__global__ void k_rk2(RbxScene S, int stage, double dt, int fix_q7, double skin) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= S.n_bodies) return;
   const int i3 = 3 * b, i9 = 9 * b;
@@ -168,6 +182,7 @@ __global__ void k_rk2(RbxScene S, int stage, double dt, int fix_q7) {
   matvec3(S.iinv_g + i9, L, om);
 #pragma unroll
   for (int j = 0; j < 3; j++) S.omega[i3 + j] = om[j];
+  check_displacement(S, b, skin);
 }
 
 __global__ void k_pose(RbxScene S, int flags) {
@@ -215,10 +230,10 @@ __global__ void k_pose(RbxScene S, int flags) {
   }
 }
 
-int launch_bodies(const RbxScene *S, int mode, double dt, cudaStream_t st) {
+int launch_bodies(const RbxScene *S, int mode, double dt, double skin, cudaStream_t st) {
   if (S->n_bodies <= 0) return RBX_OK;
   const int T = 128;
-  k_bodies<<<rbx_blocks((long long)S->n_bodies * 32, T), T, 0, st>>>(*S, mode, dt);
+  k_bodies<<<rbx_blocks((long long)S->n_bodies * 32, T), T, 0, st>>>(*S, mode, dt, skin);
   RBX_CHECK_LAUNCH();
   return RBX_OK;
 }
@@ -227,17 +242,17 @@ int launch_bodies(const RbxScene *S, int mode, double dt, cudaStream_t st) {
 
 extern "C" int rbx_reduce_bodies(const RbxScene *scene, void *stream) {
   if (!scene) return RBX_ERR_INVALID;
-  return launch_bodies(scene, 1, 0., (cudaStream_t)stream);
+  return launch_bodies(scene, 1, 0., 0., (cudaStream_t)stream);
 }
 
 extern "C" int rbx_gtvf_kick(const RbxScene *scene, double dt, void *stream) {
   if (!scene) return RBX_ERR_INVALID;
-  return launch_bodies(scene, 2, dt, (cudaStream_t)stream);
+  return launch_bodies(scene, 2, dt, 0., (cudaStream_t)stream);
 }
 
-extern "C" int rbx_gtvf_drift(const RbxScene *scene, double dt, void *stream) {
+extern "C" int rbx_gtvf_drift(const RbxScene *scene, double dt, double skin, void *stream) {
   if (!scene) return RBX_ERR_INVALID;
-  return launch_bodies(scene, 4, dt, (cudaStream_t)stream);
+  return launch_bodies(scene, 4, dt, skin, (cudaStream_t)stream);
 }
 
 extern "C" int rbx_pose_particles(const RbxScene *scene, int flags, void *stream) {
@@ -250,11 +265,11 @@ extern "C" int rbx_pose_particles(const RbxScene *scene, int flags, void *stream
 }
 
 extern "C" int rbx_rk2_stage(const RbxScene *scene, int stage, double dt, int fix_q7,
-                             void *stream) {
+                             double skin, void *stream) {
   if (!scene || stage < 0 || stage > 2) return RBX_ERR_INVALID;
   if (!scene->xcm0 || !scene->vcm0 || !scene->ang_mom0 || !scene->R0) return RBX_ERR_INVALID;
   if (scene->n_bodies <= 0) return RBX_OK;
-  k_rk2<<<rbx_blocks(scene->n_bodies, 128), 128, 0, (cudaStream_t)stream>>>(*scene, stage, dt, fix_q7);
+  k_rk2<<<rbx_blocks(scene->n_bodies, 128), 128, 0, (cudaStream_t)stream>>>(*scene, stage, dt, fix_q7, skin);
   RBX_CHECK_LAUNCH();
   return RBX_OK;
 }
@@ -268,13 +283,13 @@ extern "C" int rbx_gtvf_step(const RbxScene *scene, const RbxPoints *src, const 
   if (!scene || !src || !cells || !params) return RBX_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
-  if ((rc = launch_bodies(scene, 8 | 4, params->dt, st))) return rc;
+  if ((rc = launch_bodies(scene, 8 | 4, params->dt, params->skin, st))) return rc;
   if ((rc = rbx_pose_particles(scene, RBX_POSE_POS | RBX_POSE_VEL | RBX_POSE_VEL_PREV |
                                           RBX_POSE_NORMALS, stream))) return rc;
   if ((rc = rbx_cells_build(src, cells, params->reach, scene->status, workspace,
                             workspace_bytes, stream))) return rc;
   if ((rc = rbx_contact_mofidi(scene, cells, params, nullptr, stream))) return rc;
-  if ((rc = launch_bodies(scene, 1 | 2, params->dt, st))) return rc;
+  if ((rc = launch_bodies(scene, 1 | 2, params->dt, 0., st))) return rc;
   if (!(flags & 1))
     if ((rc = rbx_pose_particles(scene, RBX_POSE_VEL, stream))) return rc;
   return RBX_OK;

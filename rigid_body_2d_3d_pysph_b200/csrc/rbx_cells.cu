@@ -21,8 +21,11 @@ constexpr int kScanThreads = 256;
 constexpr int kScanItems = 8;
 constexpr int kScanTile = kScanThreads * kScanItems;
 
+#define RBX_SKIP_IF_VALID(C) do { if ((C).cond && *(C).cond == 0u) return; } while (0)
+
 __global__ void k_bounds(RbxPoints P, RbxCells C, double min_cell, BoundsWS *ws,
                          uint32_t *status) {
+  RBX_SKIP_IF_VALID(C);
   double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < P.n; k += gridDim.x * blockDim.x) {
     int g = P.index ? P.index[k] : k;
@@ -83,21 +86,26 @@ __global__ void k_bounds(RbxPoints P, RbxCells C, double min_cell, BoundsWS *ws,
   }
 }
 
+// The per-point passes use capped grids with grid-stride loops: when the
+// neighbour lists are still valid (cond == 0) a skipped build costs a few
+// hundred CTAs per kernel instead of one per 256 points.
 __global__ void k_count(RbxPoints P, RbxCells C, int32_t *counts) {
-  int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= P.n) return;
+  RBX_SKIP_IF_VALID(C);
   const RbxGridInfo gi = *C.info;
-  int g = P.index ? P.index[k] : k;
-  int cx = rbx_cell_coord(P.x[g], gi.x0, gi.inv_cell, gi.nx);
-  int cy = rbx_cell_coord(P.y[g], gi.y0, gi.inv_cell, gi.ny);
-  int cz = rbx_cell_coord(P.z[g], gi.z0, gi.inv_cell, gi.nz);
-  int c = (cz * gi.ny + cy) * gi.nx + cx;
-  C.cell_of[k] = c;
-  C.rank[k] = atomicAdd(&counts[c], 1);
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < P.n; k += gridDim.x * blockDim.x) {
+    int g = P.index ? P.index[k] : k;
+    int cx = rbx_cell_coord(P.x[g], gi.x0, gi.inv_cell, gi.nx);
+    int cy = rbx_cell_coord(P.y[g], gi.y0, gi.inv_cell, gi.ny);
+    int cz = rbx_cell_coord(P.z[g], gi.z0, gi.inv_cell, gi.nz);
+    int c = (cz * gi.ny + cy) * gi.nx + cx;
+    C.cell_of[k] = c;
+    C.rank[k] = atomicAdd(&counts[c], 1);
+  }
 }
 
 // ---- exclusive scan of n int32 (three passes, fixed launch geometry) ----
-__global__ void k_scan_tiles(const int32_t *in, int32_t *out, int32_t *tile_sum, int n) {
+__global__ void k_scan_tiles(RbxCells C, const int32_t *in, int32_t *out, int32_t *tile_sum, int n) {
+  RBX_SKIP_IF_VALID(C);
   __shared__ int32_t wsum[kScanThreads / 32];
   int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
   int32_t v[kScanItems];
@@ -127,7 +135,8 @@ __global__ void k_scan_tiles(const int32_t *in, int32_t *out, int32_t *tile_sum,
   if (threadIdx.x == kScanThreads - 1) tile_sum[blockIdx.x] = run;
 }
 
-__global__ void k_scan_sums(int32_t *tile_sum, int ntiles) {
+__global__ void k_scan_sums(RbxCells C, int32_t *tile_sum, int ntiles) {
+  RBX_SKIP_IF_VALID(C);
   // one block; sequential carry over chunks of blockDim.x tiles
   __shared__ int32_t wsum[32];
   __shared__ int32_t carry_s;
@@ -154,7 +163,8 @@ __global__ void k_scan_sums(int32_t *tile_sum, int ntiles) {
   }
 }
 
-__global__ void k_scan_add(int32_t *out, const int32_t *tile_sum, int n) {
+__global__ void k_scan_add(RbxCells C, int32_t *out, const int32_t *tile_sum, int n) {
+  RBX_SKIP_IF_VALID(C);
   int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
   int32_t off = tile_sum[blockIdx.x];
 #pragma unroll
@@ -163,21 +173,23 @@ __global__ void k_scan_add(int32_t *out, const int32_t *tile_sum, int n) {
 }
 
 __global__ void k_scatter(RbxPoints P, RbxCells C) {
-  int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= P.n) return;
-  int g = P.index ? P.index[k] : k;
-  C.gidx[C.cell_start[C.cell_of[k]] + C.rank[k]] = g;
+  RBX_SKIP_IF_VALID(C);
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < P.n; k += gridDim.x * blockDim.x) {
+    int g = P.index ? P.index[k] : k;
+    C.gidx[C.cell_start[C.cell_of[k]] + C.rank[k]] = g;
+  }
 }
 
 // Arrival order inside a cell depends on atomic timing; sorting each cell's
 // few entries by global index makes the list (and every sum over it)
 // reproducible, and gives the lowest-index tie rule for free.
 __global__ void k_sort_cells(RbxCells C) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C.info->ncells) return;
+  RBX_SKIP_IF_VALID(C);
+  const int ncells = C.info->ncells;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncells; c += gridDim.x * blockDim.x) {
   int s = C.cell_start[c], e = C.cell_start[c + 1];
   int n = e - s;
-  if (n < 2) return;
+  if (n < 2) continue;
   int32_t *a = C.gidx + s;
   if (n <= 64) {
     for (int i = 1; i < n; i++) {
@@ -211,17 +223,19 @@ __global__ void k_sort_cells(RbxCells C) {
       }
     }
   }
+  }
 }
 
 __global__ void k_gather(RbxPoints P, RbxCells C) {
-  int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= P.n) return;
-  int g = C.gidx[k];
-  C.sx[k] = P.x[g];
-  C.sy[k] = P.y[g];
-  C.sz[k] = P.z[g];
-  C.sh[k] = P.h[g];
-  C.sdem[k] = P.dem_id[g];
+  RBX_SKIP_IF_VALID(C);
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < P.n; k += gridDim.x * blockDim.x) {
+    int g = C.gidx[k];
+    C.sx[k] = P.x[g];
+    C.sy[k] = P.y[g];
+    C.sz[k] = P.z[g];
+    C.sh[k] = P.h[g];
+    C.sdem[k] = P.dem_id[g];
+  }
 }
 
 // ---- parity mode: enumerate NNPS neighbours of dst points -----------------
@@ -292,13 +306,17 @@ extern "C" int rbx_cells_build(const RbxPoints *pts, const RbxCells *cells, doub
   const int T = 256;
   int nb = rbx_blocks(pts->n, T);
   int bb = nb < 148 * 8 ? nb : 148 * 8;
+  nb = nb < 148 * 16 ? nb : 148 * 16;     // grid-stride loops
   k_bounds<<<bb, T, 0, st>>>(*pts, *cells, min_cell, bws, status);
   k_count<<<nb, T, 0, st>>>(*pts, *cells, counts);
-  k_scan_tiles<<<ntiles, kScanThreads, 0, st>>>(counts, cells->cell_start, tile_sum, nscan);
-  k_scan_sums<<<1, 1024, 0, st>>>(tile_sum, ntiles);
-  k_scan_add<<<ntiles, kScanThreads, 0, st>>>(cells->cell_start, tile_sum, nscan);
+  k_scan_tiles<<<ntiles, kScanThreads, 0, st>>>(*cells, counts, cells->cell_start, tile_sum, nscan);
+  k_scan_sums<<<1, 1024, 0, st>>>(*cells, tile_sum, ntiles);
+  k_scan_add<<<ntiles, kScanThreads, 0, st>>>(*cells, cells->cell_start, tile_sum, nscan);
   k_scatter<<<nb, T, 0, st>>>(*pts, *cells);
-  k_sort_cells<<<rbx_blocks(cells->cap_cells, T), T, 0, st>>>(*cells);
+  {
+    int ns = rbx_blocks(cells->cap_cells, T);
+    k_sort_cells<<<ns < 148 * 16 ? ns : 148 * 16, T, 0, st>>>(*cells);
+  }
   k_gather<<<nb, T, 0, st>>>(*pts, *cells);
   RBX_CHECK_LAUNCH();
   return RBX_OK;

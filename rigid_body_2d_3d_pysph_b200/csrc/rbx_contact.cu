@@ -58,11 +58,12 @@ constexpr int kWarps = RBX_CHUNK / 32;
 constexpr int kBatch = 4;        // staged candidates per thread per iteration
 constexpr int kPre = RBX_KPRE;   // list entries in flight per thread in k_slots
 
-template <bool UNIFORM_H>
 __global__ void __launch_bounds__(RBX_CHUNK, RBX_NB_MINB)
-k_neighbours(RbxScene S, RbxCells C, RbxParams P, double reach, double h_uniform) {
+k_neighbours(RbxScene S, RbxCells C, RbxParams P, double reach) {
+  // `reach` here is the LIST radius = neighbour reach + skin.  The list is a
+  // superset of the neighbour set; k_slots applies the exact predicate.
+  if (S.rebuild && *S.rebuild == 0u) return;      // lists still valid
   __shared__ double t_x[RBX_TILE], t_y[RBX_TILE], t_z[RBX_TILE];
-  __shared__ double t_h[UNIFORM_H ? 1 : RBX_TILE];
   __shared__ int t_pos[RBX_TILE], t_dem[RBX_TILE];
   __shared__ double red[kWarps][6];
   __shared__ int wtot[2][kBatch][kWarps];
@@ -71,16 +72,19 @@ k_neighbours(RbxScene S, RbxCells C, RbxParams P, double reach, double h_uniform
   __shared__ int range[6];
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int chunk = blockIdx.x;
+  const RbxGridInfo gi = *C.info;
+  const size_t n_rigid = (size_t)S.n_rigid;
+  // persistent CTAs over the chunks: a skipped evaluation then costs one
+  // wave of CTAs, not one CTA per chunk
+  for (int chunk = blockIdx.x; chunk < S.n_chunks; chunk += gridDim.x) {
+  __syncthreads();              // shared memory of the previous chunk is free
   const int p0 = S.chunk_start[chunk], p1 = S.chunk_start[chunk + 1];
   const int p = p0 + tid;
   const bool valid = p < p1;
   const int my_dem = S.dem_id[p0];
-  const RbxGridInfo gi = *C.info;
-  const size_t n_rigid = (size_t)S.n_rigid;
 
-  double px = 0, py = 0, pz = 0, ph = 0;
-  if (valid) { px = S.x[p]; py = S.y[p]; pz = S.z[p]; ph = S.h[p]; }
+  double px = 0, py = 0, pz = 0;
+  if (valid) { px = S.x[p]; py = S.y[p]; pz = S.z[p]; }
 
   // ---- 1. chunk bounding box --------------------------------------------
   {
@@ -125,14 +129,12 @@ k_neighbours(RbxScene S, RbxCells C, RbxParams P, double reach, double h_uniform
   unsigned long long ncand = 0;
   const int cap = S.list_cap;
 
-  const double rs2 = P.radius_scale * P.radius_scale;
-  const double hi2 = rbx_h2(rs2, ph);
-  const double hj2_u = rbx_h2(rs2, h_uniform);
+  const double rl2 = reach * reach;
 
   int tile_cnt = 0;
   int it = 0;
 
-  // ---- 3. exact predicate against the staged tile -------------------------
+  // ---- 3. list predicate against the staged tile ---------------------------
   auto phase_a = [&]() {
     __syncthreads();  // tile complete
     if (valid) {
@@ -140,10 +142,7 @@ k_neighbours(RbxScene S, RbxCells C, RbxParams P, double reach, double h_uniform
 #pragma unroll 4
       for (int j = 0; j < tile_cnt; j++) {
         const double r2 = rbx_r2(px - t_x[j], py - t_y[j], pz - t_z[j]);
-        bool hit = r2 < hi2;
-        if (!UNIFORM_H) hit = hit || (r2 < rbx_h2(rs2, t_h[j]));
-        else hit = hit || (r2 < hj2_u);
-        if (hit) {
+        if (r2 < rl2) {
           if (nlist < cap) {
             S.nbr_pos[(size_t)nlist * n_rigid + p] = t_pos[j];
             S.nbr_dem[(size_t)nlist * n_rigid + p] = t_dem[j];
@@ -194,8 +193,8 @@ k_neighbours(RbxScene S, RbxCells C, RbxParams P, double reach, double h_uniform
     for (int base = 0; base < total; base += kBatch * RBX_CHUNK) {
       if (tile_cnt + kBatch * RBX_CHUNK > RBX_TILE) phase_a();
       bool keep[kBatch];
-      double sx[kBatch], sy[kBatch], sz[kBatch], sh[kBatch];
-      int sd[kBatch], sq[kBatch];
+      double sx[kBatch], sy[kBatch], sz[kBatch];
+      int sd[kBatch], sq[kBatch], sg[kBatch];
 #pragma unroll
       for (int k = 0; k < kBatch; k++) {
         const int f = base + k * RBX_CHUNK + tid;
@@ -216,8 +215,8 @@ k_neighbours(RbxScene S, RbxCells C, RbxParams P, double reach, double h_uniform
       for (int k = 0; k < kBatch; k++) {
         if (sq[k] >= 0) {
           sd[k] = C.sdem[sq[k]];
+          sg[k] = C.gidx[sq[k]];
           sx[k] = C.sx[sq[k]]; sy[k] = C.sy[sq[k]]; sz[k] = C.sz[sq[k]];
-          if (!UNIFORM_H) sh[k] = C.sh[sq[k]];
         }
       }
       const int buf = it & 1;
@@ -244,8 +243,7 @@ k_neighbours(RbxScene S, RbxCells C, RbxParams P, double reach, double h_uniform
         if (keep[k]) {
           const int dst = off + __popc(bal[k] & ((1u << lane) - 1u));
           t_x[dst] = sx[k]; t_y[dst] = sy[k]; t_z[dst] = sz[k];
-          if (!UNIFORM_H) t_h[dst] = sh[k];
-          t_pos[dst] = sq[k]; t_dem[dst] = sd[k];
+          t_pos[dst] = sg[k]; t_dem[dst] = sd[k];   // global index, dem_id
         }
       }
       tile_cnt = run;
@@ -258,7 +256,7 @@ k_neighbours(RbxScene S, RbxCells C, RbxParams P, double reach, double h_uniform
     S.nbr_cnt[p] = nlist;
     if (list_overflow && S.status) atomicOr(S.status, RBX_STATUS_LIST_OVERFLOW);
   }
-  // counters: gated in-range pairs, candidate tests
+  // counters: candidate distance tests, list entries written
   if (S.counters) {
     unsigned long long g = (unsigned long long)nlist, c = ncand;
 #pragma unroll
@@ -266,8 +264,25 @@ k_neighbours(RbxScene S, RbxCells C, RbxParams P, double reach, double h_uniform
       g += __shfl_xor_sync(0xffffffffu, g, o);
       c += __shfl_xor_sync(0xffffffffu, c, o);
     }
-    if (lane == 0) { atomicAdd(&S.counters[0], g); atomicAdd(&S.counters[2], c); }
+    if (lane == 0) { atomicAdd(&S.counters[2], c); atomicAdd(&S.counters[3], g); }
   }
+  }  // chunk loop
+}
+
+// After a rebuild: remember where every body was, then lower the flag.
+__global__ void k_list_commit(RbxScene S) {
+  if (!S.rebuild || *S.rebuild == 0u || !S.xcm_ref) return;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= S.n_bodies) return;
+#pragma unroll
+  for (int j = 0; j < 3; j++) S.xcm_ref[3 * b + j] = S.xcm[3 * b + j];
+#pragma unroll
+  for (int k = 0; k < 9; k++) S.R_ref[9 * b + k] = S.R[9 * b + k];
+}
+
+__global__ void k_list_clear(RbxScene S, double skin) {
+  // skin == 0: no reuse, the flag stays up and every evaluation rebuilds
+  if (S.rebuild && S.xcm_ref && skin > 0.) *S.rebuild = 0u;
 }
 
 constexpr int kAcc = RBX_KACC;  // slots accumulated per pass over the list
@@ -293,7 +308,7 @@ k_slots(RbxScene S, RbxCells C, RbxParams P, RbxDiag D, double h_uniform) {
   const size_t n_rigid = (size_t)S.n_rigid;
 
   double fx = 0, fy = 0, fz = 0, px = 0, py = 0, pz = 0;
-  unsigned nactive = 0;
+  unsigned nactive = 0, npairs = 0;
   if (valid) {
     px = S.x[p]; py = S.y[p]; pz = S.z[p];
     const double ph = S.h[p];
@@ -308,6 +323,9 @@ k_slots(RbxScene S, RbxCells C, RbxParams P, RbxDiag D, double h_uniform) {
     const double hij_u = 0.5 * (ph + h_uniform);
     const double rmin0 = 4. * spacing0;              // :765
     const double vol = md / rhod;
+    const double rs2 = P.radius_scale * P.radius_scale;
+    const double hi2 = rbx_h2(rs2, ph);
+    const double hj2_u = rbx_h2(rs2, h_uniform);
 
     int nout = 0, ki = 0;
     // A particle touching more than kAcc bodies takes further rounds; the
@@ -325,7 +343,7 @@ k_slots(RbxScene S, RbxCells C, RbxParams P, RbxDiag D, double h_uniform) {
       int nk = 0;
       bool overflow = false;       // some key did not fit this round
       // software pipeline over the list, kPre entries per stage:
-      //   stage L: list loads (dem, pos)        for batch b + 2
+      //   stage L: list loads (dem, global idx) for batch b + 2
       //   stage G: position gathers             for batch b + 1
       //   stage C: pair math + accumulation     for batch b
       // so that the two dependent memory round trips (list -> gather) of
@@ -351,8 +369,8 @@ k_slots(RbxScene S, RbxCells C, RbxParams P, RbxDiag D, double h_uniform) {
 #pragma unroll
       for (int k = 0; k < kPre; k++) {
         if (ddG[k] >= 0) {
-          gx[k] = C.sx[qqG[k]]; gy[k] = C.sy[qqG[k]]; gz[k] = C.sz[qqG[k]];
-          if (!UNIFORM_H) gh[k] = C.sh[qqG[k]];
+          gx[k] = S.x[qqG[k]]; gy[k] = S.y[qqG[k]]; gz[k] = S.z[qqG[k]];
+          if (!UNIFORM_H) gh[k] = S.h[qqG[k]];
         }
       }
       load_lists(kPre, ddL, qqL);
@@ -368,8 +386,8 @@ k_slots(RbxScene S, RbxCells C, RbxParams P, RbxDiag D, double h_uniform) {
 #pragma unroll
         for (int k = 0; k < kPre; k++) {       // stage G for batch b + 1
           if (ddG[k] >= 0) {
-            gx[k] = C.sx[qqG[k]]; gy[k] = C.sy[qqG[k]]; gz[k] = C.sz[qqG[k]];
-            if (!UNIFORM_H) gh[k] = C.sh[qqG[k]];
+            gx[k] = S.x[qqG[k]]; gy[k] = S.y[qqG[k]]; gz[k] = S.z[qqG[k]];
+            if (!UNIFORM_H) gh[k] = S.h[qqG[k]];
           }
         }
         load_lists(e0 + 2 * kPre, ddL, qqL);   // stage L for batch b + 2
@@ -377,6 +395,12 @@ k_slots(RbxScene S, RbxCells C, RbxParams P, RbxDiag D, double h_uniform) {
         for (int k = 0; k < kPre; k++) {
           const int d = dd[k];
           if (d < 0) continue;
+          const double x0 = px - sx[k], x1 = py - sy[k], x2 = pz - sz[k];
+          const double r2 = rbx_r2(x0, x1, x2);
+          // exact neighbour predicate on the list entry:
+          // the list was built with a skin, possibly several steps ago
+          if (!(r2 < hi2 || r2 < (UNIFORM_H ? hj2_u : rbx_h2(rs2, sh[k])))) continue;
+          if (n_served == 0) npairs++;
           // slot of this key (first come, first served)
           int sl = -1;
 #pragma unroll
@@ -396,13 +420,11 @@ k_slots(RbxScene S, RbxCells C, RbxParams P, RbxDiag D, double h_uniform) {
               continue;
             }
           }
-          const double x0 = px - sx[k], x1 = py - sy[k], x2 = pz - sz[k];
           // 1/r from rsqrt (1 ulp) instead of sqrt + division: the sums
           // below move by a few ulp (tolerance 1e-10), the dependent FP64
           // chain per entry is 3x shorter.  The closest-point decision, which
           // must match the CPU path bit for bit, still compares correctly
           // rounded sqrt values (below).
-          const double r2 = rbx_r2(x0, x1, x2);
           const double rinv = rsqrt(r2);
           const double rij = r2 * rinv;
           const double hij = UNIFORM_H ? hij_u : 0.5 * (ph + sh[k]);
@@ -426,7 +448,7 @@ k_slots(RbxScene S, RbxCells C, RbxParams P, RbxDiag D, double h_uniform) {
             const double rmin = (pg.x >= 0) ? sqrt(acc[sl][7][tid]) : rmin0;
             bool take = rex < rmin;
             if (!take && pg.x >= 0 && rex == rmin)     // exact tie: lowest
-              take = C.gidx[qq[k]] < C.gidx[pg.x];     // global index wins
+              take = qq[k] < pg.x;                     // global index wins
             if (take) {
               acc[sl][7][tid] = r2;                      // exact r2 of the best
               acc[sl][8][tid] = r2;
@@ -469,7 +491,7 @@ k_slots(RbxScene S, RbxCells C, RbxParams P, RbxDiag D, double h_uniform) {
         double dist = 0.;
         if (a_w2 > 1e-12) dist = (nx * a_bx + ny * a_by + nz * a_bz) / a_w2;
         double vxs = 0., vys = 0., vzs = 0.;
-        const int gmin = pg.x >= 0 ? C.gidx[pg.x] : -1;
+        const int gmin = pg.x;                 // global index (-1: none)
         if (pg.x >= 0) { vxs = S.u[gmin]; vys = S.v[gmin]; vzs = S.w[gmin]; }
 
         // previous state of this slot
@@ -598,10 +620,14 @@ k_slots(RbxScene S, RbxCells C, RbxParams P, RbxDiag D, double h_uniform) {
     for (int a = 0; a < 6; a++) S.chunk_ft[((size_t)chunk * kWarps + wid) * 6 + a] = v6[a];
   }
   if (S.counters) {
-    unsigned na = nactive;
+    unsigned na = nactive, np_ = npairs;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) na += __shfl_xor_sync(0xffffffffu, na, o);
+    for (int o = 16; o > 0; o >>= 1) {
+      na += __shfl_xor_sync(0xffffffffu, na, o);
+      np_ += __shfl_xor_sync(0xffffffffu, np_, o);
+    }
     if (lane == 0 && na) atomicAdd(&S.counters[1], (unsigned long long)na);
+    if (lane == 0 && np_) atomicAdd(&S.counters[0], (unsigned long long)np_);
   }
 }
 
@@ -622,10 +648,15 @@ extern "C" int rbx_contact_neighbours(const RbxScene *scene, const RbxCells *cel
   if (scene->n_chunks <= 0) return RBX_OK;
   cudaStream_t st = (cudaStream_t)stream_;
   const int nb = scene->n_chunks;
-  if (params->h_uniform > 0.)
-    k_neighbours<true><<<nb, RBX_CHUNK, 0, st>>>(*scene, *cells, *params, params->reach, params->h_uniform);
-  else
-    k_neighbours<false><<<nb, RBX_CHUNK, 0, st>>>(*scene, *cells, *params, params->reach, 0.);
+  if (params->skin < 0.) return RBX_ERR_INVALID;
+  {
+    const int grid = nb < 148 * RBX_NB_MINB * 4 ? nb : 148 * RBX_NB_MINB * 4;
+    k_neighbours<<<grid, RBX_CHUNK, 0, st>>>(*scene, *cells, *params, params->reach + params->skin);
+  }
+  if (scene->rebuild) {
+    k_list_commit<<<rbx_blocks(scene->n_bodies, 256), 256, 0, st>>>(*scene);
+    k_list_clear<<<1, 1, 0, st>>>(*scene, params->skin);
+  }
   RBX_CHECK_LAUNCH();
   return RBX_OK;
 }

@@ -54,7 +54,7 @@ class DeviceScene(object):
     def __init__(self, arrays, rigid_names, boundary_names=(), dim=3,
                  kr=1e5, kf=1e3, fric_coeff=0.5, gx=0., gy=0., gz=0.,
                  planar=False, ks=8, radius_scale=3.0, eta_uniform=None,
-                 cap_cells=None, list_cap=96, device=None):
+                 cap_cells=None, list_cap=96, skin_factor=0.05, device=None):
         if not torch.cuda.is_available():
             raise _lib.RbxError('DeviceScene needs a CUDA device; the '
                                 'rigid-body path has no CPU fallback')
@@ -69,6 +69,10 @@ class DeviceScene(object):
         self.planar = bool(planar)
         self.ks = int(ks)
         self.list_cap = int(list_cap)
+        # neighbour lists are built with reach * (1 + skin_factor) and reused
+        # until a body has moved more than half the skin; 0 rebuilds them at
+        # every force evaluation (the reference's NNPS.update every step)
+        self.skin_factor = float(skin_factor)
         self.radius_scale = float(radius_scale)
         self.kr, self.kf, self.fric_coeff = float(kr), float(kf), \
             float(fric_coeff)
@@ -173,6 +177,17 @@ class DeviceScene(object):
             sp.append(np.full(nb, float(pa.constants['spacing0'][0])))
         self.B['spacing0'] = self._t(np.concatenate(sp) if sp
                                      else np.zeros(0), f64)
+        # list reuse: where every body was at the last build, and how far a
+        # particle of it can be from the centre of mass
+        self.B['xcm_ref'] = self.B['xcm'].clone()
+        self.B['R_ref'] = self.B['R'].clone()
+        r0 = torch.sqrt(self.P['dx0']**2 + self.P['dy0']**2 +
+                        self.P['dz0']**2)
+        rmax = torch.zeros(max(self.n_bodies, 1), dtype=f64, device=dev)
+        if self.n_rigid:
+            rmax.scatter_reduce_(0, self.P['body'].long(), r0, 'amax')
+        self.B['rmax'] = rmax
+        self.rebuild = torch.ones(1, dtype=i32, device=dev)
         # ---- chunks ----------------------------------------------------
         counts = np.bincount(body, minlength=self.n_bodies) \
             if body.size else np.zeros(self.n_bodies, np.int64)
@@ -233,6 +248,7 @@ class DeviceScene(object):
         hmin = float(h.min().item()) if h.numel() else 1.0
         self.h_uniform = self.hmax if hmin == self.hmax else 0.0
         self.reach = self.radius_scale * self.hmax
+        self.skin = self.skin_factor * self.reach
         # ---- history, status, counters ---------------------------------
         nr = max(self.n_rigid, 1)
         self.H = []
@@ -304,6 +320,9 @@ class DeviceScene(object):
         s.iinv_g = _ptr(B['inertia_tensor_inverse_global_frame'])
         s.status = _ptr(self.status)
         s.counters = _ptr(self.counters)
+        s.rebuild = _ptr(self.rebuild)
+        s.xcm_ref, s.R_ref = _ptr(B['xcm_ref']), _ptr(B['R_ref'])
+        s.rmax = _ptr(B['rmax'])
         self._scene = [None, None]
         for par in (0, 1):
             c = RbxScene.from_buffer_copy(s)
@@ -319,8 +338,10 @@ class DeviceScene(object):
         for n in ['info', 'cell_start', 'cell_of', 'rank', 'gidx', 'sx', 'sy',
                   'sz', 'sh', 'sdem']:
             setattr(c, n, _ptr(self.C[n]))
+        c.cond = _ptr(self.rebuild)     # skip the build while lists are valid
         self._cells = c
         self._graph = None
+        self.rebuild.fill_(1)
 
     def points(self, index=None, n=None):
         p = RbxPoints()
@@ -337,7 +358,11 @@ class DeviceScene(object):
     def params(self, dt):
         return RbxParams(self.radius_scale, self.kr, self.kf,
                          self.fric_coeff, self.g[0], self.g[1], self.g[2],
-                         float(dt), self.reach, self.h_uniform)
+                         float(dt), self.reach, self.h_uniform, self.skin)
+
+    def force_rebuild(self):
+        """Neighbour lists must be rebuilt at the next force evaluation."""
+        self.rebuild.fill_(1)
 
     @property
     def stream(self):
@@ -394,6 +419,8 @@ class DeviceScene(object):
                 host = pa.properties[name] if name in pa.properties else \
                     pa.constants[name]
                 t.copy_(torch.as_tensor(host, dtype=t.dtype))
+                if name in ('x', 'y', 'z', 'xcm', 'R'):
+                    self.rebuild.fill_(1)      # positions changed under us
             touched.clear()
         if rebuild:
             for pa in self.arrays:
@@ -451,7 +478,8 @@ class DeviceScene(object):
 
     def gtvf_drift(self, dt):
         _lib.check(self.lib.rbx_gtvf_drift(ctypes.byref(self.scene),
-                                           float(dt), self.stream), 'drift')
+                                           float(dt), self.skin, self.stream),
+                   'drift')
 
     def pose(self, flags):
         _lib.check(self.lib.rbx_pose_particles(ctypes.byref(self.scene),
@@ -461,7 +489,7 @@ class DeviceScene(object):
     def rk2_stage(self, stage, dt, fix_q7=False):
         _lib.check(self.lib.rbx_rk2_stage(ctypes.byref(self.scene),
                                           int(stage), float(dt), int(fix_q7),
-                                          self.stream), 'rk2')
+                                          self.skin, self.stream), 'rk2')
 
     def _gtvf_step_call(self, p, flags=0):
         _lib.check(self.lib.rbx_gtvf_step(
@@ -549,7 +577,7 @@ class DeviceScene(object):
         if reset:
             self.counters.zero_()
         return {'gated_pairs': int(c[0]), 'active_slots': int(c[1]),
-                'candidates': int(c[2])}
+                'candidates': int(c[2]), 'list_entries': int(c[3])}
 
     def grid_info(self):
         raw = self.C['info'].cpu().numpy().tobytes()
@@ -597,6 +625,7 @@ class DeviceScene(object):
         for n in ['info', 'cell_start', 'cell_of', 'rank', 'gidx', 'sx', 'sy',
                   'sz', 'sh', 'sdem']:
             setattr(c, n, _ptr(self.C[n]))
+        c.cond = None
         self.cells_build(self.points(sidx), c)
         dpts = self.points(didx)
         counts = torch.zeros(max(dn, 1), dtype=torch.int32, device=dev)

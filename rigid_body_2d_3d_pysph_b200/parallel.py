@@ -19,9 +19,13 @@ the exchange stays correct even when bodies drift across the initial cuts
 (ownership does not migrate; only the efficiency of the slabs would degrade).
 Static wall particles are replicated per slab when the scene is built.
 
-Per step and rank: one all_gather of 2 doubles (interest interval), one
-all_gather of `world` counts, and point-to-point payload messages only
-between ranks whose intervals overlap (the two slab neighbours).
+Neighbour lists are reused across steps (device.py, skin), so the halo must
+keep its identity between list rebuilds: a *full* exchange (interest intervals
+padded by the skin, fresh selection, counts) happens only on the steps where
+the lists are rebuilt -- a global decision, one all_reduce(MAX) of the
+device-side rebuild flag per step -- and the steps in between only refresh the
+positions and velocities of the same particles in the same halo slots
+(point-to-point payload between slab neighbours, no selection, no counts).
 """
 import numpy as np
 import torch
@@ -83,7 +87,7 @@ def exchange_rows(cols, rows, rank, world, group=None):
         for req in dist.batch_isend_irecv(ops):
             req.wait()
     got = torch.cat(recv, 0) if recv else cols[:0]
-    return got, int(counts.sum()), int(sum(recv_counts))
+    return got, int(table[rank].sum()), int(sum(recv_counts)), table
 
 
 class SlabScene(object):
@@ -102,6 +106,8 @@ class SlabScene(object):
             'halo array must be last and fully source-flagged'
         self.own_src = src[src < scene.n_rigid]
         self.n_halo = 0
+        self._send_idx = None
+        self._send_counts = self._recv_counts = None
         self.bytes_sent = 0
         self.bytes_recv = 0
         self._set_source_count(0)
@@ -110,22 +116,39 @@ class SlabScene(object):
         self.n_halo = n_halo
         self.sc._src.n = self.n_src_static + n_halo
 
-    def exchange_halo(self):
+    def lists_need_rebuild(self):
+        """Global decision (all ranks rebuild together): has any body on any
+        rank moved more than half the skin since the lists were built?"""
+        flag = self.sc.rebuild
+        if self.world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
+        return bool(flag.item() != 0)          # host sync
+
+    def exchange_halo(self, full=True):
+        """full: choose afresh which source particles every rank needs
+        (interest intervals padded by the skin) and remember the choice;
+        otherwise only refresh positions and velocities of the particles
+        chosen at the last full exchange -- same particles, same halo slots,
+        so neighbour lists that name them stay valid."""
         sc = self.sc
         P = sc.P
-        iv = interest_interval(P['x'][:sc.n_rigid], sc.reach)
+        if not full and self._send_idx is not None:
+            self._refresh_halo()
+            return
+        iv = interest_interval(P['x'][:sc.n_rigid], sc.reach + sc.skin)
         if self.world > 1:
             ivs = [torch.empty_like(iv) for _ in range(self.world)]
             dist.all_gather(ivs, iv, group=self.group)
             ivs = torch.stack(ivs)
         else:
             ivs = iv[None, :]
-        ivh = ivs.cpu()                      # host sync 1 (2 doubles / rank)
-        # my sources lie inside my own interval shrunk by the reach; only
+        ivh = ivs.cpu()                      # host sync (2 doubles / rank)
+        # my sources lie inside my own interval shrunk by its padding; only
         # ranks whose interval overlaps that can want any of them (the two
         # slab neighbours unless bodies have wandered)
-        lo_own = float(ivh[self.rank, 0]) + sc.reach
-        hi_own = float(ivh[self.rank, 1]) - sc.reach
+        pad = sc.reach + sc.skin
+        lo_own = float(ivh[self.rank, 0]) + pad
+        hi_own = float(ivh[self.rank, 1]) - pad
         idx = self.own_src
         xs = P['x'][idx]
         rows = []
@@ -136,29 +159,65 @@ class SlabScene(object):
                 rows.append(empty)
                 continue
             rows.append(torch.nonzero((xs >= lo_q) & (xs <= hi_q)).flatten())
-        sel = torch.cat(rows)
-        gsel = idx[sel]
-        cols = torch.stack([P['x'][gsel], P['y'][gsel], P['z'][gsel],
-                            P['u'][gsel], P['v'][gsel], P['w'][gsel],
-                            P['h'][gsel], P['dem_id'][gsel].double()], 1)
+        gsel = idx[torch.cat(rows)]
+        cols = self._pack(gsel)
         # rows of `cols` per destination are consecutive blocks
         offs = np.cumsum([0] + [r.numel() for r in rows])
         rel = [torch.arange(int(offs[q]), int(offs[q + 1]), device=xs.device)
                for q in range(self.world)]
         if self.world > 1:
-            got, ns, nr = exchange_rows(cols, rel, self.rank, self.world,
-                                        self.group)
+            got, ns, nr, table = exchange_rows(cols, rel, self.rank,
+                                               self.world, self.group)
         else:
-            got, ns, nr = cols[:0], 0, 0
+            got, ns, nr, table = cols[:0], 0, 0, None
         if nr > self.halo_cap:
             raise _lib.RbxError('halo capacity %d < %d received particles' %
                                 (self.halo_cap, nr))
+        self._send_idx = gsel
+        self._send_counts = [int(offs[q + 1] - offs[q])
+                             for q in range(self.world)]
+        self._recv_counts = [int(table[q, self.rank]) if table is not None
+                             else 0 for q in range(self.world)]
+        self._unpack(got, nr)
+        self._set_source_count(nr)
+        self.bytes_sent += ns * HALO_COLS * 8
+        self.bytes_recv += nr * HALO_COLS * 8
+
+    def _pack(self, gsel):
+        P = self.sc.P
+        return torch.stack([P['x'][gsel], P['y'][gsel], P['z'][gsel],
+                            P['u'][gsel], P['v'][gsel], P['w'][gsel],
+                            P['h'][gsel], P['dem_id'][gsel].double()], 1)
+
+    def _unpack(self, got, nr):
+        P = self.sc.P
         o = self.halo_off
         for c, n in enumerate(['x', 'y', 'z', 'u', 'v', 'w', 'h']):
             P[n][o:o + nr] = got[:, c]
         P['dem_id'][o:o + nr] = got[:, 7].to(torch.int32)
-        self._set_source_count(nr)
-        self.bytes_sent += ns * HALO_COLS * 8
+
+    def _refresh_halo(self):
+        cols = self._pack(self._send_idx)
+        dev = cols.device
+        send = list(torch.split(cols, self._send_counts, 0))
+        recv = [torch.empty(n, HALO_COLS, dtype=cols.dtype, device=dev)
+                for n in self._recv_counts]
+        ops = []
+        for q in range(self.world):
+            if q == self.rank:
+                continue
+            if self._send_counts[q] > 0:
+                ops.append(dist.P2POp(dist.isend, send[q].contiguous(), q,
+                                      self.group))
+            if self._recv_counts[q] > 0:
+                ops.append(dist.P2POp(dist.irecv, recv[q], q, self.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        nr = sum(self._recv_counts)
+        if nr:
+            self._unpack(torch.cat(recv, 0), nr)
+        self.bytes_sent += sum(self._send_counts) * HALO_COLS * 8
         self.bytes_recv += nr * HALO_COLS * 8
 
     def gtvf_step(self, dt, nsteps=1):
@@ -171,7 +230,7 @@ class SlabScene(object):
             sc.gtvf_drift(dt)
             sc.pose(_lib.POSE_POS | _lib.POSE_VEL | _lib.POSE_VEL_PREV |
                     _lib.POSE_NORMALS)
-            self.exchange_halo()
+            self.exchange_halo(full=self.lists_need_rebuild())
             sc.cells_build()
             sc.contact(dt)
             sc.reduce_bodies()

@@ -183,3 +183,33 @@ def test_graph_replay_equals_eager():
         if pa.name in meta['rigid']:
             for n in ('x', 'y', 'z', 'fx', 'fy', 'fz', 'xcm', 'R'):
                 assert np.array_equal(getattr(pa, n), getattr(pb, n)), n
+
+
+@pytest.mark.parametrize('name', ['cubes3d', 'collide2d'])
+def test_list_reuse_does_not_change_results(name):
+    """Neighbour lists built with a skin and reused across steps give the
+    same forces as lists rebuilt at every evaluation (k_slots applies the
+    exact predicate to every entry), and they are in fact reused."""
+    res = {}
+    for skin in (0.0, 0.05, 0.25):
+        arrays, ref, meta = load_case(name)
+        sc = _scene(arrays, meta, skin_factor=skin, list_cap=192)
+        sc.gtvf_step(meta['dt'], meta['nsteps'])
+        sc.check_status()
+        res[skin] = (arrays, sc.read_counters())
+    base, cbase = res[0.0]
+    for skin in (0.05, 0.25):
+        arrays, cnt = res[skin]
+        assert cnt['gated_pairs'] == cbase['gated_pairs'], skin
+        assert cnt['list_entries'] < 0.5 * cbase['list_entries'], \
+            (skin, cnt, cbase)
+        for pa, pb in zip(arrays, base):
+            if pa.name not in meta['rigid']:
+                continue
+            f = np.sqrt(pb.fx**2 + pb.fy**2 + pb.fz**2).sum()
+            for n in ('fx', 'fy', 'fz'):
+                assert_close(getattr(pa, n), getattr(pb, n), 1e-11,
+                             '%s skin %g %s' % (name, skin, n), max(f, 1e-300))
+            for n in ('xcm', 'R'):
+                assert_close(getattr(pa, n), getattr(pb, n), 1e-12,
+                             '%s skin %g %s' % (name, skin, n), 1.0)

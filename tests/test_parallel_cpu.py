@@ -46,7 +46,7 @@ def _worker(rank, world, port, q):
         dist.all_gather(ivs, iv)
         ivs = torch.stack(ivs)
         rows = parallel.select_halo(cols, ivs, rank)
-        got, ns, nr = parallel.exchange_rows(cols, rows, rank, world)
+        got, ns, nr, _ = parallel.exchange_rows(cols, rows, rank, world)
         # expectation from the other slab, built locally
         other, _, _ = synthetic_pile(NB, slab=(1 - rank, world))
         oc = _cols(other[0]).numpy()

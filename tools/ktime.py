@@ -4,21 +4,31 @@ sys.path.insert(0,'/root/repo')
 from rigid_body_2d_3d_pysph_b200 import _lib
 from rigid_body_2d_3d_pysph_b200.device import DeviceScene
 from rigid_body_2d_3d_pysph_b200.scenes import synthetic_pile
-nb=int(sys.argv[1]); settle=int(sys.argv[2])
+nb=int(sys.argv[1]); settle=int(sys.argv[2]); skin=float(sys.argv[4]) if len(sys.argv)>4 else 0.1
 (body, wall), scheme, info = synthetic_pile(nb)
-sc = DeviceScene([body, wall], ['body'], ['wall'], dim=3, gy=-9.81, eta_uniform=info['eta_uniform'])
+sc = DeviceScene([body, wall], ['body'], ['wall'], dim=3, gy=-9.81, eta_uniform=info['eta_uniform'], skin_factor=skin)
 sc.gtvf_step(1e-4, settle, graph=True)
 torch.cuda.synchronize()
 p = sc.params(1e-4)
-ev=[torch.cuda.Event(enable_timing=True) for _ in range(3)]
-t1=[];t2=[]
+ev=[torch.cuda.Event(enable_timing=True) for _ in range(4)]
+t0=[];t1=[];t2=[];t3=[]
 for i in range(8):
-    sc.cells_build()
+    sc.force_rebuild()
     ev[0].record()
+    sc.cells_build()
+    ev[1].record()
+    _lib.check(sc.lib.rbx_contact_neighbours(ctypes.byref(sc.scene), ctypes.byref(sc._cells), ctypes.byref(p), sc.stream))
+    ev[2].record()
+    _lib.check(sc.lib.rbx_contact_slots(ctypes.byref(sc.scene), ctypes.byref(sc._cells), ctypes.byref(p), None, sc.stream))
+    ev[3].record()
+    torch.cuda.synchronize()
+    t0.append(ev[0].elapsed_time(ev[1])); t1.append(ev[1].elapsed_time(ev[2])); t2.append(ev[2].elapsed_time(ev[3]))
+    # no rebuild: K1 skipped
+    ev[0].record()
+    sc.cells_build()
     _lib.check(sc.lib.rbx_contact_neighbours(ctypes.byref(sc.scene), ctypes.byref(sc._cells), ctypes.byref(p), sc.stream))
     ev[1].record()
-    _lib.check(sc.lib.rbx_contact_slots(ctypes.byref(sc.scene), ctypes.byref(sc._cells), ctypes.byref(p), None, sc.stream))
-    ev[2].record()
     torch.cuda.synchronize()
-    t1.append(ev[0].elapsed_time(ev[1])); t2.append(ev[1].elapsed_time(ev[2]))
-print('%s  K1 %.3f ms  K2 %.3f ms' % (sys.argv[3] if len(sys.argv)>3 else '', np.mean(t1[2:]), np.mean(t2[2:])))
+    t3.append(ev[0].elapsed_time(ev[1]))
+cnt = sc.T['nbr_cnt'].float()
+print('%s skin=%.2f cells %.3f ms  K1 %.3f ms  K2 %.3f ms  skipped(cells+K1) %.3f ms  list mean %.1f max %d' % (sys.argv[3] if len(sys.argv)>3 else '', skin, np.mean(t0[2:]), np.mean(t1[2:]), np.mean(t2[2:]), np.mean(t3[2:]), cnt.mean().item(), int(cnt.max().item())))
