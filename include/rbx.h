@@ -120,8 +120,7 @@ typedef struct {
   const int32_t *chunk_start; /* [n_chunks + 1] particle ranges          */
   const int32_t *chunk_body;  /* [n_chunks]                              */
   const int32_t *body_chunk;  /* [n_bodies + 1] chunk ranges per body    */
-  double *chunk_ft;           /* [n_chunks * 4 * 6] per-warp partial
-                                 force, torque                           */
+  double *chunk_ft;           /* reserved (unused)                       */
   /* Neighbour lists, [list_cap][n_rigid]: global index and dem_id of every
    * gated source within reach + skin of the particle when the list was
    * built; nbr_cnt[n_rigid] entries per particle.  Built by
@@ -229,8 +228,7 @@ int rbx_pairs_dump(const RbxPoints *dst, const RbxCells *cells,
 
 /* ComputeContactForceNormals + ComputeContactForceDistanceAndClosestPoint +
  * BodyForce + ComputeContactForce (rigid_body_common.py:631-1032, :115-125),
- * fused, with sparse slots, plus the per-chunk partial sums of
- * SumUpExternalForces (:128-175).  Reads history *_in, writes *_out.       */
+ * fused, with sparse slots.  Reads history *_in, writes *_out and fx,fy,fz. */
 int rbx_contact_mofidi(const RbxScene *scene, const RbxCells *cells,
                        const RbxParams *params, const RbxDiag *diag,
                        void *stream);
@@ -244,8 +242,9 @@ int rbx_contact_slots(const RbxScene *scene, const RbxCells *cells,
                       const RbxParams *params, const RbxDiag *diag,
                       void *stream);
 
-/* SumUpExternalForces.reduce (rigid_body_common.py:128-175): chunk partials
- * -> force[3nb], torque[3nb] in a fixed order (deterministic).             */
+/* SumUpExternalForces.reduce (rigid_body_common.py:128-175): fx,fy,fz,x,y,z
+ * -> force[3nb], torque[3nb], one warp per body, fixed order
+ * (deterministic).                                                        */
 int rbx_reduce_bodies(const RbxScene *scene, void *stream);
 
 /* GTVFRigidBody{3D,2D}Step.py_stage1 / py_stage3 (rigid_body_3d.py:41-60,

@@ -1,6 +1,6 @@
 // Per-body kernels: force/torque reduction and the rigid steppers, plus the
 // per-particle pose kernel.  One warp per body for the reduction (lanes
-// stride over the body's chunk partials, fixed shuffle tree => deterministic);
+// stride over the body's particles, fixed shuffle tree => deterministic);
 // the 3x3 algebra of a body is done by lane 0 (a few hundred flops).
 //
 //   SumUpExternalForces.reduce        rigid_body_common.py:128-175
@@ -129,12 +129,18 @@ __global__ void k_bodies(RbxScene S, int mode, double dt, double skin) {
   if (warp >= S.n_bodies) return;
   const int b = warp;
   if (mode & 1) {
+    // SumUpExternalForces.reduce :158-175: lanes stride over the body's
+    // particles (contiguous), fixed shuffle tree => deterministic
     double v6[6] = {0, 0, 0, 0, 0, 0};
-    // four warp partials per chunk (rbx_contact.cu, k_slots)
-    const int c0 = 4 * S.body_chunk[b], c1 = 4 * S.body_chunk[b + 1];
-    for (int c = c0 + lane; c < c1; c += 32) {
-#pragma unroll
-      for (int a = 0; a < 6; a++) v6[a] += S.chunk_ft[(size_t)c * 6 + a];
+    const int q0 = S.chunk_start[S.body_chunk[b]], q1 = S.chunk_start[S.body_chunk[b + 1]];
+    const double cx = S.xcm[3 * b], cy = S.xcm[3 * b + 1], cz = S.xcm[3 * b + 2];
+    for (int q = q0 + lane; q < q1; q += 32) {
+      const double fx = S.fx[q], fy = S.fy[q], fz = S.fz[q];
+      const double dx = S.x[q] - cx, dy = S.y[q] - cy, dz = S.z[q] - cz;
+      v6[0] += fx; v6[1] += fy; v6[2] += fz;
+      v6[3] += (dy * fz - dz * fy);
+      v6[4] += (dz * fx - dx * fz);
+      v6[5] += (dx * fy - dy * fx);
     }
 #pragma unroll
     for (int a = 0; a < 6; a++) v6[a] = rbx_warp_sum(v6[a]);

@@ -5,7 +5,6 @@
 //   ComputeContactForceDistanceAndClosestPoint  rigid_body_common.py:726-836
 //   BodyForce.initialize                        rigid_body_common.py:115-125
 //   ComputeContactForce.post_loop               rigid_body_common.py:839-1032
-//   SumUpExternalForces.reduce (warp partials)  rigid_body_common.py:128-175
 //
 // Two launches over the same decomposition: one CTA per "chunk" (<= 128
 // consecutive particles of one rigid body, thread t <-> particle p0 + t).
@@ -27,8 +26,8 @@
 //      the reference's two pair loops collapse into one -- then applies the
 //      spring/dashpot/Coulomb law with the history carried in the sparse
 //      slot table,
-//   5. warp-shuffle reduction of force and torque about the body's centre of
-//      mass -> one partial per warp (fixed order, deterministic).
+//   5. writes fx, fy, fz; k_bodies (rbx_bodies.cu) sums them per body with a
+//      fixed shuffle tree (deterministic).
 #include "rbx_common.cuh"
 #include <string.h>
 
@@ -295,16 +294,14 @@ k_slots(RbxScene S, RbxCells C, RbxParams P, RbxDiag D, double h_uniform) {
   // register indexing.  Field 9 packs (pmin, gmin) as two ints.
   __shared__ double acc[kAcc][kFields][RBX_CHUNK];
 
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int chunk = blockIdx.x;
-  const int p0 = S.chunk_start[chunk], p1 = S.chunk_start[chunk + 1];
-  if (p0 + wid * 32 >= p1) {   // whole warp beyond the chunk: zero partial
-    if (lane < 6) S.chunk_ft[((size_t)chunk * kWarps + wid) * 6 + lane] = 0.;
-    return;
-  }
-  const int p = p0 + tid;
-  const bool valid = p < p1;
-  const int body = S.chunk_body[chunk];
+  // flat decomposition: thread <-> rigid particle, full warps regardless of
+  // the body sizes (a body of 100 particles would leave a quarter of the
+  // lanes of a 128-thread chunk idle, and this kernel is latency bound per
+  // warp).  The per-body force/torque sum is done by k_bodies from fx,fy,fz.
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int p = blockIdx.x * RBX_CHUNK + tid;
+  const bool valid = p < S.n_rigid;
+  const int body = valid ? S.body[p] : 0;
   const size_t n_rigid = (size_t)S.n_rigid;
 
   double fx = 0, fy = 0, fz = 0, px = 0, py = 0, pz = 0;
@@ -603,22 +600,6 @@ k_slots(RbxScene S, RbxCells C, RbxParams P, RbxDiag D, double h_uniform) {
     S.fx[p] = fx; S.fy[p] = fy; S.fz[p] = fz;
   }
 
-  // ---- 5. warp partial of SumUpExternalForces :158-175 ---------------------
-  double v6[6] = {0, 0, 0, 0, 0, 0};
-  if (valid) {
-    const double dx = px - S.xcm[3 * body], dy = py - S.xcm[3 * body + 1],
-                 dz = pz - S.xcm[3 * body + 2];
-    v6[0] = fx; v6[1] = fy; v6[2] = fz;
-    v6[3] = dy * fz - dz * fy;
-    v6[4] = dz * fx - dx * fz;
-    v6[5] = dx * fy - dy * fx;
-  }
-#pragma unroll
-  for (int a = 0; a < 6; a++) v6[a] = rbx_warp_sum(v6[a]);
-  if (lane == 0) {
-#pragma unroll
-    for (int a = 0; a < 6; a++) S.chunk_ft[((size_t)chunk * kWarps + wid) * 6 + a] = v6[a];
-  }
   if (S.counters) {
     unsigned na = nactive, np_ = npairs;
 #pragma unroll
@@ -670,13 +651,13 @@ extern "C" int rbx_contact_slots(const RbxScene *scene, const RbxCells *cells,
   RbxDiag d;
   if (diag) d = *diag; else memset(&d, 0, sizeof(d));
   const bool uni = params->h_uniform > 0.;
-  const int nb = scene->n_chunks;
+  const int ng = rbx_blocks(scene->n_rigid, RBX_CHUNK);
   if (scene->dim == 3) {
-    if (uni) k_slots<3, true><<<nb, RBX_CHUNK, 0, st>>>(*scene, *cells, *params, d, params->h_uniform);
-    else k_slots<3, false><<<nb, RBX_CHUNK, 0, st>>>(*scene, *cells, *params, d, 0.);
+    if (uni) k_slots<3, true><<<ng, RBX_CHUNK, 0, st>>>(*scene, *cells, *params, d, params->h_uniform);
+    else k_slots<3, false><<<ng, RBX_CHUNK, 0, st>>>(*scene, *cells, *params, d, 0.);
   } else {
-    if (uni) k_slots<2, true><<<nb, RBX_CHUNK, 0, st>>>(*scene, *cells, *params, d, params->h_uniform);
-    else k_slots<2, false><<<nb, RBX_CHUNK, 0, st>>>(*scene, *cells, *params, d, 0.);
+    if (uni) k_slots<2, true><<<ng, RBX_CHUNK, 0, st>>>(*scene, *cells, *params, d, params->h_uniform);
+    else k_slots<2, false><<<ng, RBX_CHUNK, 0, st>>>(*scene, *cells, *params, d, 0.);
   }
   RBX_CHECK_LAUNCH();
   return RBX_OK;

@@ -201,8 +201,7 @@ class DeviceScene(object):
         self.T = {'chunk_start': self._t(cs, i32),
                   'chunk_body': self._t(cb, i32),
                   'body_chunk': self._t(bc, i32),
-                  'chunk_ft': torch.zeros(max(self.n_chunks, 1) * 24,
-                                          dtype=f64, device=dev)}
+                  'chunk_ft': None}
         # neighbour lists [list_cap][n_rigid] (scratch of the contact op)
         nr_ = max(self.n_rigid, 1)
         self.T['nbr_pos'] = torch.empty(self.list_cap * nr_, dtype=i32,
