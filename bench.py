@@ -301,15 +301,16 @@ def main():
     except Exception:
         pass
     roof = {'bound': 'hbm',
-            'kernel': 'contact evaluation = k_neighbours + k_slots '
-            '(rbx_contact_mofidi; k_slots is the longer of the two)',
+            'kernel': 'contact evaluation (rbx_contact_mofidi): k_slots, plus '
+            'k_neighbours on the steps that rebuild the neighbour lists',
             'achieved': contact_b / (contact_ms * 1e-3) / 1e9, 'peak': peak,
             'unit': 'GB/s', 'peak_source': peak_src, 'traffic': traffic,
             'traffic_source': 'profiles/r01_traffic.json (ncu dram__bytes '
             'read+write of both launches)' if traffic else None,
-            'secondary_limiter': 'FP64 pipe / issue (k_neighbours 43 % FP64, '
-            '70 % issue active) and latency (k_slots 24 % FP64, 43 % issue '
-            'active): see profiles/',
+            'secondary_limiter': 'latency (k_slots: 25 % FP64 pipe, 46 % issue '
+            'active, 16 warps/SM at 128 registers) and FP64 issue '
+            '(k_neighbours: 36 % FP64 pipe, 63 % issue active): see '
+            'profiles/',
             'ms_per_launch': contact_ms,
             'ms_per_launch_with_list_rebuild': contact_rebuild_ms,
             'algorithmic_bytes_per_launch': contact_b}
@@ -387,9 +388,12 @@ def main():
                    min(args.settle, args.cpu_settle), args.cpu_steps)}
 
     if rank == 0:
-        launches_per_step = 14   # bodies, pose, 8 cell-list kernels,
-        #                          k_neighbours, k_slots, bodies, pose
-        #                          (memsets not counted)
+        launches_per_step = 16   # bodies, pose, 8 cell-list kernels,
+        #                          k_neighbours, list commit + clear,
+        #                          k_slots, bodies, pose (memsets not
+        #                          counted; the cell-list kernels and
+        #                          k_neighbours return at once on steps
+        #                          that reuse the neighbour lists)
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT,
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
