@@ -102,6 +102,8 @@ def install(force=False):
     except ImportError:
         class _Plt(types.ModuleType):
             def __getattr__(self, name):
+                if name.startswith('__'):
+                    raise AttributeError(name)
                 return lambda *a, **k: _Plt('x')
         mpl = _module('matplotlib')
         mpl.__path__ = []

@@ -42,3 +42,25 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
         assert 'no CPU fallback' in str(e)
     else:
         raise AssertionError('load() must raise when librbx.so is missing')
+
+
+def test_reference_script_runs_to_the_device_boundary():
+    """An unmodified reference script, run through the compat layer, gets all
+    the way to building the device scene and then fails LOUDLY without a GPU
+    (no CPU fallback).  Skipped where /root/reference is absent (GPU box)."""
+    import subprocess
+    import sys
+    import pytest
+    script = '/root/reference/code/benchmark_2_multiple_rigid_bodies_colliding.py'
+    if not os.path.exists(script):
+        pytest.skip('reference not mounted')
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present: covered by the gpu tests')
+    _ensure_built()
+    out = subprocess.run(
+        [sys.executable, '-m', 'rigid_body_2d_3d_pysph_b200.run', script,
+         '--tf', '0.001', '--disable-output'], cwd=ROOT,
+        capture_output=True, text=True, timeout=600)
+    assert out.returncode != 0
+    assert 'no CPU fallback' in out.stderr, out.stderr[-2000:]
