@@ -1,0 +1,169 @@
+"""Edge cases of the CUDA path against the oracle: non-uniform h (the other
+template instantiation), bodies larger than one 128-particle chunk, ragged
+bodies, capacity overflows reported through the status word, empty pieces."""
+import numpy as np
+import pytest
+
+from oracle import rbo
+from rigid_body_2d_3d_pysph_b200.compat.particle_array import \
+    get_particle_array
+from tests.util import DENSE_SLOTS, assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _make(dim, bodies, wall, h_body, h_wall, rho=2000., spacing=0.05):
+    """bodies: list of (x, y, z) arrays, one rigid array holding all."""
+    from rigid_body_2d_3d_pysph_b200.rigid_body_3d import RigidBody3DScheme
+    x = np.concatenate([b[0] for b in bodies])
+    y = np.concatenate([b[1] for b in bodies])
+    z = np.concatenate([b[2] for b in bodies])
+    bid = np.concatenate([np.full(len(b[0]), k) for k, b in enumerate(bodies)])
+    nb = len(bodies)
+    body = get_particle_array(name='body', x=x, y=y, z=z, h=h_body,
+                              m=rho * spacing**dim, rho=rho,
+                              constants={'spacing0': spacing})
+    body.add_property('body_id', type='int', data=bid)
+    body.add_property('dem_id', type='int', data=bid)
+    body.add_constant('total_no_bodies', [nb + 1])
+    arrays = [body]
+    bounds = []
+    if wall is not None:
+        w = get_particle_array(name='wall', x=wall[0], y=wall[1], z=wall[2],
+                               h=h_wall, m=rho * spacing**dim, rho=rho)
+        w.add_property('dem_id', type='int', data=nb)
+        arrays.append(w)
+        bounds = ['wall']
+    s = RigidBody3DScheme(['body'], bounds, dim=dim, gy=-9.81)
+    s.kf = 1e3
+    s.setup_properties(arrays)
+    for pa in arrays:
+        pa.add_property('contact_force_is_boundary')
+        pa.contact_force_is_boundary[:] = pa.is_boundary[:]
+    if wall is not None:
+        arrays[1].contact_force_is_boundary[:] = 1.
+    return arrays, s
+
+
+def _clone(arrays):
+    out = []
+    for pa in arrays:
+        q = get_particle_array(name=pa.name)
+        q.__dict__['_n'] = pa.get_number_of_particles()
+        for n, v in pa.properties.items():
+            q.add_property(n, type=pa.property_types[n], data=v,
+                           stride=pa.stride[n])
+        for n, v in pa.constants.items():
+            q.add_constant(n, v)
+        out.append(q)
+    return out
+
+
+def _run_both(arrays, s, dim, dt, nsteps, **kw):
+    from rigid_body_2d_3d_pysph_b200.device import DeviceScene
+    oarr = _clone(arrays)
+    for pa in oarr[:1]:
+        tnb = int(pa.total_no_bodies[0])
+        for n in DENSE_SLOTS:
+            if n not in pa.properties:
+                pa.add_property(n, stride=tnb)
+        if 'dem_id_source' not in pa.properties:
+            pa.add_property('dem_id_source', type='int', stride=tnb)
+    sc = DeviceScene(arrays, ['body'], [a.name for a in arrays[1:]], dim=dim,
+                     kr=s.kr, kf=s.kf, fric_coeff=s.fric_coeff, gx=s.gx,
+                     gy=s.gy, gz=s.gz, **kw)
+    p = rbo.make_params(dim, dt, s.kr, s.kf, s.fric_coeff, s.gx, s.gy, s.gz)
+    sc.gtvf_step(dt, nsteps)
+    rbo.gtvf_step(oarr, ['body'], p, nsteps=nsteps)
+    sc.check_status()
+    g, o = arrays[0], oarr[0]
+    f = np.sqrt(o.fx**2 + o.fy**2 + o.fz**2).sum()
+    for n in ('fx', 'fy', 'fz', 'force'):
+        assert_close(getattr(g, n), getattr(o, n), 1e-10, n, max(f, 1e-300))
+    for n in ('xcm', 'R', 'vcm', 'omega', 'x', 'y'):
+        assert_close(getattr(g, n), getattr(o, n), 1e-9, n,
+                     max(np.abs(getattr(o, n)).max(), 1e-2))
+    return sc, g, o
+
+
+def _block2d(nx, ny, dx, x0, y0):
+    i, j = np.meshgrid(np.arange(nx), np.arange(ny), indexing='ij')
+    return x0 + i.ravel() * dx, y0 + j.ravel() * dx, np.zeros(nx * ny)
+
+
+def test_nonuniform_h_and_multi_chunk_body():
+    """A 20x20 body (400 particles = 4 chunks) and a ragged 3x7 one on a wall
+    whose particles carry a different h (non-uniform-h kernel variants; the
+    neighbour predicate then really uses max(h_i, h_j))."""
+    dx = 0.05
+    b1 = _block2d(20, 20, dx, 0.0, 0.0)
+    b2 = _block2d(3, 7, dx, 20 * dx + 0.9 * dx, 0.0)
+    xw = (np.arange(60) - 10) * dx
+    wall = (xw, np.full(60, -0.97 * dx), np.zeros(60))
+    arrays, s = _make(2, [b1, b2], wall, h_body=dx, h_wall=1.2 * dx)
+    sc, g, o = _run_both(arrays, s, 2, 1e-4, 30)
+    assert sc.h_uniform == 0.0 and sc.n_chunks == 5
+    assert np.abs(o.fy).max() > 1.0          # the wall is felt
+
+
+def test_no_boundaries_no_neighbours():
+    """Two bodies far apart, no boundary arrays at all: empty source sets for
+    every slot, free fall."""
+    dx = 0.05
+    arrays, s = _make(2, [_block2d(4, 4, dx, 0., 0.),
+                          _block2d(4, 4, dx, 5., 0.)], None, dx, dx)
+    sc, g, o = _run_both(arrays, s, 2, 1e-4, 20)
+    assert sc.read_counters()['active_slots'] == 0
+    # GTVF: no initial acceleration, so the first half kick uses F = 0
+    assert np.allclose(g.vcm.reshape(-1, 3)[:, 1], -9.81 * 19.5e-4)
+
+
+def test_neighbour_list_overflow_is_reported():
+    from rigid_body_2d_3d_pysph_b200 import _lib
+    from rigid_body_2d_3d_pysph_b200.device import DeviceScene
+    dx = 0.05
+    b1 = _block2d(6, 6, dx, 0.0, 0.0)
+    xw = (np.arange(30) - 10) * dx
+    wall = (xw, np.full(30, -0.97 * dx), np.zeros(30))
+    arrays, s = _make(2, [b1], wall, dx, dx)
+    sc = DeviceScene(arrays, ['body'], ['wall'], dim=2, gy=-9.81, list_cap=2)
+    sc.gtvf_step(1e-4, 1)
+    with pytest.raises(_lib.RbxError, match='neighbour list overflow'):
+        sc.check_status()
+
+
+def test_history_overflow_is_reported():
+    """ks = 1 but a corner particle is in contact with the floor and a second
+    body at once."""
+    from rigid_body_2d_3d_pysph_b200 import _lib
+    from rigid_body_2d_3d_pysph_b200.device import DeviceScene
+    dx = 0.05
+    b1 = _block2d(4, 4, dx, 0.0, 0.0)
+    b2 = _block2d(4, 4, dx, 4 * dx - 0.35 * dx, 0.0)
+    xw = (np.arange(30) - 10) * dx
+    wall = (xw, np.full(30, -0.9 * dx), np.zeros(30))
+    arrays, s = _make(2, [b1, b2], wall, dx, dx)
+    sc = DeviceScene(arrays, ['body'], ['wall'], dim=2, gy=-9.81, ks=1)
+    sc.gtvf_step(1e-4, 2)
+    with pytest.raises(_lib.RbxError, match='simultaneous contacts'):
+        sc.check_status()
+
+
+def test_more_than_four_source_bodies_on_one_particle():
+    """A small body surrounded by five others and the wall: its particles see
+    six source bodies, more than the kAcc = 4 slot accumulators of one pass
+    (extra rounds in k_slots)."""
+    dx = 0.05
+    g = 0.96 * dx
+    c = _block2d(2, 2, dx, 0.0, 0.0)
+    around = [(-2 * dx - g + dx, 0.0), (2 * dx + g - dx, 0.0),
+              (-2 * dx - g + dx, 2 * dx + g - dx), (2 * dx + g - dx, 2 * dx + g - dx),
+              (0.0, 2 * dx + g - dx)]
+    bodies = [c] + [_block2d(2, 2, dx, ax, ay) for ax, ay in around]
+    xw = (np.arange(30) - 15) * dx
+    wall = (xw, np.full(30, -0.97 * dx), np.zeros(30))
+    arrays, s = _make(2, bodies, wall, dx, dx)
+    sc, gg, o = _run_both(arrays, s, 2, 5e-5, 12)
+    tnb = int(o.total_no_bodies[0])
+    seen = (o.contact_force_normal_wij.reshape(-1, tnb) > 0).sum(1)
+    assert seen[:4].max() >= 5, seen[:4]
