@@ -146,8 +146,9 @@ typedef struct {
   const double *hist_dlt_in, *hist_fn_in; /* [3][ks][n_rigid] */
   int32_t *hist_key_out;
   double *hist_dlt_out, *hist_fn_out;
-  /* device status word + counters: [0] gated in-range pairs, [1] active
-   * (in-contact) slots, [2] candidate distance tests                     */
+  /* device status word + 8 counters: [0] gated in-range pairs, [1] active
+   * (in-contact) slots, [2] candidate distance tests, [3] neighbour-list
+   * entries written, [7] chunk dispenser of k_neighbours (internal)      */
   uint32_t *status;
   unsigned long long *counters;
   /* list reuse: rebuild[0] != 0 <=> lists must be rebuilt this evaluation.

@@ -73,10 +73,18 @@ k_neighbours(RbxScene S, RbxCells C, RbxParams P, double reach) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const RbxGridInfo gi = *C.info;
   const size_t n_rigid = (size_t)S.n_rigid;
-  // persistent CTAs over the chunks: a skipped evaluation then costs one
-  // wave of CTAs, not one CTA per chunk
-  for (int chunk = blockIdx.x; chunk < S.n_chunks; chunk += gridDim.x) {
+  // persistent CTAs over the chunks (a skipped evaluation then costs one
+  // wave of CTAs, not one CTA per chunk), chunks handed out dynamically
+  // through counters[7] (reset by k_list_clear) so that CTAs with dense
+  // neighbourhoods do not hold up the tail
+  __shared__ int s_chunk;
+  for (;;) {
   __syncthreads();              // shared memory of the previous chunk is free
+  if (tid == 0)
+    s_chunk = S.counters ? (int)atomicAdd(&S.counters[7], 1ull) : -1;
+  __syncthreads();
+  const int chunk = s_chunk;
+  if (chunk < 0 || chunk >= S.n_chunks) break;
   const int p0 = S.chunk_start[chunk], p1 = S.chunk_start[chunk + 1];
   const int p = p0 + tid;
   const bool valid = p < p1;
@@ -280,6 +288,7 @@ __global__ void k_list_commit(RbxScene S) {
 }
 
 __global__ void k_list_clear(RbxScene S, double skin) {
+  if (S.counters) S.counters[7] = 0ull;      // chunk dispenser of k_neighbours
   // skin == 0: no reuse, the flag stays up and every evaluation rebuilds
   if (S.rebuild && S.xcm_ref && skin > 0.) *S.rebuild = 0u;
 }
@@ -618,7 +627,7 @@ static int check_contact_args(const RbxScene *scene, const RbxCells *cells, cons
   if (!scene || !cells || !params) return RBX_ERR_INVALID;
   if (scene->ks < 1 || (scene->dim != 2 && scene->dim != 3)) return RBX_ERR_INVALID;
   if (!(params->reach > 0.) || scene->list_cap < 1) return RBX_ERR_INVALID;
-  if (!scene->nbr_pos || !scene->nbr_dem || !scene->nbr_cnt) return RBX_ERR_INVALID;
+  if (!scene->nbr_pos || !scene->nbr_dem || !scene->nbr_cnt || !scene->counters) return RBX_ERR_INVALID;
   return RBX_OK;
 }
 
@@ -634,10 +643,9 @@ extern "C" int rbx_contact_neighbours(const RbxScene *scene, const RbxCells *cel
     const int grid = nb < 148 * RBX_NB_MINB * 4 ? nb : 148 * RBX_NB_MINB * 4;
     k_neighbours<<<grid, RBX_CHUNK, 0, st>>>(*scene, *cells, *params, params->reach + params->skin);
   }
-  if (scene->rebuild) {
+  if (scene->rebuild)
     k_list_commit<<<rbx_blocks(scene->n_bodies, 256), 256, 0, st>>>(*scene);
-    k_list_clear<<<1, 1, 0, st>>>(*scene, params->skin);
-  }
+  k_list_clear<<<1, 1, 0, st>>>(*scene, params->skin);
   RBX_CHECK_LAUNCH();
   return RBX_OK;
 }

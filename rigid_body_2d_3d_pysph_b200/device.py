@@ -257,7 +257,7 @@ class DeviceScene(object):
                 'dlt': torch.zeros(3 * self.ks * nr, dtype=f64, device=dev),
                 'fn': torch.zeros(3 * self.ks * nr, dtype=f64, device=dev)})
         self.status = torch.zeros(1, dtype=i32, device=dev)
-        self.counters = torch.zeros(4, dtype=torch.int64, device=dev)
+        self.counters = torch.zeros(8, dtype=torch.int64, device=dev)
         # ---- cell list over the sources ----------------------------------
         self._alloc_cells(max(self.n_src, 1), self.T['src_index'])
         self._refresh_structs()
@@ -501,11 +501,15 @@ class DeviceScene(object):
         """nsteps x GTVFIntegrator.one_timestep on the device."""
         self.push_touched()
         p = self.params(dt)
+        # The stage-3 particle velocities of a step are overwritten by stage 1
+        # of the next one before anything reads them: inside a batch only the
+        # last step writes them (flag bit 0 of rbx_gtvf_step).
         if graph and nsteps >= 4:
             self._run_graph(p, nsteps)
+            self.pose(_lib.POSE_VEL)
         else:
-            for _ in range(nsteps):
-                self._gtvf_step_call(p)
+            for k in range(nsteps):
+                self._gtvf_step_call(p, flags=0 if k == nsteps - 1 else 1)
         self.steps_done += nsteps
         self.mark_device_newer()
 
@@ -519,12 +523,12 @@ class DeviceScene(object):
             s = torch.cuda.Stream(self.device)
             s.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(s):
-                self._gtvf_step_call(p)     # warm-up outside capture
-                self._gtvf_step_call(p)
+                self._gtvf_step_call(p, 1)     # warm-up outside capture
+                self._gtvf_step_call(p, 1)
                 s.synchronize()
                 with torch.cuda.graph(g, stream=s):
-                    self._gtvf_step_call(p)
-                    self._gtvf_step_call(p)
+                    self._gtvf_step_call(p, 1)
+                    self._gtvf_step_call(p, 1)
             torch.cuda.current_stream(self.device).wait_stream(s)
             assert self.parity == start
             self._graph = (key, g)
@@ -534,7 +538,7 @@ class DeviceScene(object):
             g.replay()
             nsteps -= 2
         for _ in range(nsteps):
-            self._gtvf_step_call(p)
+            self._gtvf_step_call(p, 1)
 
     def rk2_step(self, dt, nsteps=1, fix_q7=False):
         """EPEC sequencing with the RK2 stepper."""
@@ -574,7 +578,7 @@ class DeviceScene(object):
     def read_counters(self, reset=False):
         c = self.counters.cpu().numpy().copy()
         if reset:
-            self.counters.zero_()
+            self.counters[:4].zero_()
         return {'gated_pairs': int(c[0]), 'active_slots': int(c[1]),
                 'candidates': int(c[2]), 'list_entries': int(c[3])}
 
