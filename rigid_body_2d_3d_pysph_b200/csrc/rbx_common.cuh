@@ -57,9 +57,12 @@ __device__ __forceinline__ double rbx_quintic(double rij, double h) {
   double val;
   if (q > 3.0) val = 0.0;
   else {
-    val = t3 * t3 * t3 * t3 * t3;
-    if (q <= 2.0) val -= 6.0 * t2 * t2 * t2 * t2 * t2;
-    if (q <= 1.0) val += 15. * t1 * t1 * t1 * t1 * t1;
+    // x^5 as (x^2)^2 x: three multiplies instead of four (the CPU path
+    // multiplies left to right; the difference is one rounding, 1e-16)
+    const double a3 = t3 * t3, a2 = t2 * t2, a1 = t1 * t1;
+    val = a3 * a3 * t3;
+    if (q <= 2.0) val -= 6.0 * (a2 * a2 * t2);
+    if (q <= 1.0) val += 15. * (a1 * a1 * t1);
   }
   return val * fac;
 }

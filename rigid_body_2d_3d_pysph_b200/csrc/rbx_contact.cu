@@ -347,6 +347,7 @@ k_slots(RbxScene S, RbxCells C, RbxParams P, RbxDiag D, double h_uniform) {
 #pragma unroll
       for (int k = 0; k < kAcc; k++) keys[k] = 0x7fffffff;
       int nk = 0;
+      int last_key = -1, last_sl = -1;
       bool overflow = false;       // some key did not fit this round
       // software pipeline over the list, kPre entries per stage:
       //   stage L: list loads (dem, global idx) for batch b + 2
@@ -357,14 +358,18 @@ k_slots(RbxScene S, RbxCells C, RbxParams P, RbxDiag D, double h_uniform) {
       int ddL[kPre], qqL[kPre];            // loaded lists, batch b + 1 / b + 2
       int ddG[kPre], qqG[kPre];            // batch whose gathers are in flight
       double gx[kPre], gy[kPre], gz[kPre], gh[kPre];
+      // cursors into the two list planes, advanced by kPre entries per call
+      // (no 64-bit index multiply per load)
+      const int *cdem = ldem, *cpos = lpos;
       auto load_lists = [&](int e0, int *dd_, int *qq_) {
 #pragma unroll
         for (int k = 0; k < kPre; k++) {
-          const int e = e0 + k;
-          const bool in = e < nlist;
-          dd_[k] = in ? ldem[(size_t)e * n_rigid] : -1;
-          qq_[k] = in ? lpos[(size_t)e * n_rigid] : 0;
+          const bool in = e0 + k < nlist;
+          dd_[k] = in ? cdem[(size_t)k * n_rigid] : -1;
+          qq_[k] = in ? cpos[(size_t)k * n_rigid] : 0;
         }
+        cdem += (size_t)kPre * n_rigid;
+        cpos += (size_t)kPre * n_rigid;
         if (n_served) {
 #pragma unroll
           for (int k = 0; k < kPre; k++)
@@ -407,10 +412,13 @@ k_slots(RbxScene S, RbxCells C, RbxParams P, RbxDiag D, double h_uniform) {
           // the list was built with a skin, possibly several steps ago
           if (!(r2 < hi2 || r2 < (UNIFORM_H ? hj2_u : rbx_h2(rs2, sh[k])))) continue;
           if (n_served == 0) npairs++;
-          // slot of this key (first come, first served)
-          int sl = -1;
+          // slot of this key (first come, first served); entries come in
+          // runs of one source body, so try the previous entry's slot first
+          int sl = (d == last_key) ? last_sl : -1;
+          if (sl < 0) {
 #pragma unroll
-          for (int j = 0; j < kAcc; j++) if (keys[j] == d) sl = j;
+            for (int j = 0; j < kAcc; j++) if (keys[j] == d) sl = j;
+          }
           if (sl < 0) {
             if (nk < kAcc) {
               sl = nk;
@@ -431,6 +439,7 @@ k_slots(RbxScene S, RbxCells C, RbxParams P, RbxDiag D, double h_uniform) {
           // chain per entry is 3x shorter.  The closest-point decision, which
           // must match the CPU path bit for bit, still compares correctly
           // rounded sqrt values (below).
+          last_key = d; last_sl = sl;
           const double rinv = rsqrt(r2);
           const double rij = r2 * rinv;
           const double hij = UNIFORM_H ? hij_u : 0.5 * (ph + sh[k]);
