@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RBX_VERSION 100 /* 0.1.0 */
+#define RBX_VERSION 101 /* 0.1.1 */
 
 typedef enum {
   RBX_OK = 0,
@@ -120,7 +120,6 @@ typedef struct {
   const int32_t *chunk_start; /* [n_chunks + 1] particle ranges          */
   const int32_t *chunk_body;  /* [n_chunks]                              */
   const int32_t *body_chunk;  /* [n_bodies + 1] chunk ranges per body    */
-  double *chunk_ft;           /* reserved (unused)                       */
   /* Neighbour lists, [list_cap][n_rigid]: global index and dem_id of every
    * gated source within reach + skin of the particle when the list was
    * built; nbr_cnt[n_rigid] entries per particle.  Built by
@@ -128,7 +127,6 @@ typedef struct {
    * rbx_contact_slots applies the exact neighbour predicate to every entry
    * with the current positions, so the pair set is independent of the skin. */
   int32_t *nbr_pos, *nbr_dem, *nbr_cnt;
-  int32_t *chunk_perm;        /* reserved (unused)                       */
   /* per body */
   const double *total_mass, *izz, *spacing0; /* [n_bodies]               */
   double *xcm, *vcm, *ang_mom, *omega;       /* [3 n_bodies]             */

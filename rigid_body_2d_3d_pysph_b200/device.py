@@ -200,8 +200,7 @@ class DeviceScene(object):
         self.n_chunks = int(bc[-1])
         self.T = {'chunk_start': self._t(cs, i32),
                   'chunk_body': self._t(cb, i32),
-                  'body_chunk': self._t(bc, i32),
-                  'chunk_ft': None}
+                  'body_chunk': self._t(bc, i32)}
         # neighbour lists [list_cap][n_rigid] (scratch of the contact op)
         nr_ = max(self.n_rigid, 1)
         self.T['nbr_pos'] = torch.empty(self.list_cap * nr_, dtype=i32,
@@ -209,7 +208,6 @@ class DeviceScene(object):
         self.T['nbr_dem'] = torch.empty(self.list_cap * nr_, dtype=i32,
                                         device=dev)
         self.T['nbr_cnt'] = torch.zeros(nr_, dtype=i32, device=dev)
-        self.T['chunk_perm'] = torch.zeros(nr_, dtype=i32, device=dev)
         # ---- damping table ---------------------------------------------
         self.eta_mode = 0
         self.T['eta'] = None
@@ -307,9 +305,8 @@ class DeviceScene(object):
             s.normal0 = _ptr(P['normal0'])
             s.normal = _ptr(P['normal'])
         s.list_cap = self.list_cap
-        for n in ['chunk_start', 'chunk_body', 'body_chunk', 'chunk_ft',
-                  'nbr_pos', 'nbr_dem', 'nbr_cnt', 'chunk_perm', 'eta',
-                  'eta_row']:
+        for n in ['chunk_start', 'chunk_body', 'body_chunk', 'nbr_pos',
+                  'nbr_dem', 'nbr_cnt', 'eta', 'eta_row']:
             setattr(s, n, _ptr(T[n]))
         for n in ['total_mass', 'izz', 'spacing0', 'xcm', 'vcm', 'ang_mom',
                   'omega', 'force', 'torque', 'R', 'R_prev', 'xcm0', 'vcm0',
