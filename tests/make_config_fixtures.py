@@ -36,6 +36,14 @@ CONFIGS = {
                        'Dinesh2022SteadyCubesOnAWall3D', ['--pyramid-cubes']),
     'stack_of_cylinders': ('stack_of_cylinders.py', 'ZhangStackOfCylinders',
                            []),
+    # next rows of SURVEY section 8f-3 (not named by BASELINE.json)
+    'benchmark_3': (
+        'benchmark_3_multiple_rigid_bodies_colliding_same_particle_array.py',
+        'RigidFluidCoupling', []),
+    'benchmark_4': ('benchmark_4_rigid_cube_bouncing_on_a_wall.py',
+                    'RigidFluidCoupling', ['--coeff-of-restitution', '0.6']),
+    'benchmark_5_2d': ('benchmark_5_steady_cubes_on_a_wall_2d.py',
+                       'Dinesh2022SteadyCubesOnAWall2D', ['--pyramid-cubes']),
 }
 KEEP = ['x', 'y', 'z', 'u', 'v', 'w', 'h', 'm', 'rho', 'dem_id', 'body_id',
         'contact_force_is_boundary', 'is_boundary', 'normal', 'normal0',

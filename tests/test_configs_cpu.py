@@ -21,6 +21,12 @@ def test_config_sizes():
     a, m = load_config('stack_of_cylinders')
     assert a[0].get_number_of_particles() == 2541
     assert int(a[0].nb[0]) == 33 and int(a[0].total_no_bodies[0]) == 35
+    a, m = load_config('benchmark_4')
+    assert [p.get_number_of_particles() for p in a] == [162, 855]
+    assert m['stepper'] == 'gtvf2d'           # SchemeChooser default rb2d
+    assert np.count_nonzero(a[0].eta) == 6    # --coeff-of-restitution 0.6
+    a, m = load_config('benchmark_5_2d')
+    assert int(a[0].nb[0]) == 6
     # divergence D6: the command-line defaults win over constructor arguments
     assert m['kf'] == 1e3 and m['fric_coeff'] == 0.5
     # e = 0.6 for every pair (stack_of_cylinders.py:231-234)

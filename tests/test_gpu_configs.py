@@ -61,6 +61,12 @@ def _compare(name, step, garr, oarr, rigid, force_rtol, traj_rtol):
                         (50, 1e-10, 1e-9), (150, None, 1e-6)]),
     ('stack_of_cylinders', [(1, 1e-10, 1e-9), (10, 1e-10, 1e-9),
                             (200, 1e-6, 1e-6)]),
+    # the scripts BASELINE.json does not name (planar stepper,
+    # two bodies in one array over a tank; benchmark_4 with e = 0.6 damping)
+    ('benchmark_3', [(1, 1e-10, 1e-9), (10, 1e-10, 1e-9), (200, None, 1e-6)]),
+    ('benchmark_4', [(1, 1e-10, 1e-9), (10, 1e-10, 1e-9), (200, None, 1e-6)]),
+    ('benchmark_5_2d', [(1, 1e-10, 1e-9), (10, 1e-10, 1e-9),
+                        (200, None, 1e-6)]),
 ])
 def test_config_trajectory(name, checks):
     garr, meta = load_config(name)
