@@ -285,6 +285,16 @@ int rbx_contact_lvc(const RbxDemScene *scene, const RbxCells *cells,
 int rbx_dem_step(const RbxDemScene *scene, int stage, double dt,
                  void *stream);
 
+/* Setup path (one-off): boundary-particle identification of ONE array whose
+ * particles are all binned in `cells`: ComputeNormals -> SmoothNormals
+ * [upstream wall_normal; boundary_particles.py:71-135] ->
+ * IdentifyBoundaryParticleCosAngle (boundary_particles.py:22-68).  m, rho,
+ * normal_tmp[3n], normal[3n], is_boundary[n] are indexed like the points.   */
+int rbx_boundary_identify(const RbxPoints *pts, const RbxCells *cells, int dim,
+                          double radius_scale, const double *m,
+                          const double *rho, double *normal_tmp,
+                          double *normal, int32_t *is_boundary, void *stream);
+
 /* Whole GTVF step [upstream GTVFIntegrator.one_timestep, SURVEY App. C-6]:
  * kick, drift, pose, cells_build, contact, reduce, kick, velocities.
  * `src` = the source points (contact_force_is_boundary == 1) to bin.

@@ -92,7 +92,8 @@ SYMBOLS = ['rbx_version', 'rbx_strerror', 'rbx_sizeof',
            'rbx_contact_mofidi', 'rbx_contact_neighbours',
            'rbx_contact_slots', 'rbx_reduce_bodies', 'rbx_gtvf_kick',
            'rbx_gtvf_drift', 'rbx_pose_particles', 'rbx_rk2_stage',
-           'rbx_gtvf_step', 'rbx_contact_lvc', 'rbx_dem_step']
+           'rbx_gtvf_step', 'rbx_contact_lvc', 'rbx_dem_step',
+           'rbx_boundary_identify']
 
 _lib = None
 
@@ -145,6 +146,9 @@ def load():
     L.rbx_contact_lvc.argtypes = [P(RbxDemScene), P(RbxCells), P(RbxParams),
                                   c_vp]
     L.rbx_dem_step.argtypes = [P(RbxDemScene), ctypes.c_int, c_f64, c_vp]
+    L.rbx_boundary_identify.argtypes = [P(RbxPoints), P(RbxCells),
+                                        ctypes.c_int, c_f64, c_vp, c_vp, c_vp,
+                                        c_vp, c_vp, c_vp]
     for i, cls in enumerate([RbxGridInfo, RbxPoints, RbxCells, RbxScene,
                              RbxParams, RbxDiag, RbxDemScene]):
         if L.rbx_sizeof(i) != ctypes.sizeof(cls):

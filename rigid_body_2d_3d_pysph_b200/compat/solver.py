@@ -33,7 +33,10 @@ class Solver(object):
         self.particles = None
         self.scene = None
         self.output_files = []
+        # capacities / tuning of the device scene (device.py)
         self.ks = kwargs.pop('ks', 8)
+        self.list_cap = kwargs.pop('list_cap', 96)
+        self.skin_factor = kwargs.pop('skin_factor', 0.05)
         self.use_graph = kwargs.pop('use_graph', True)
         self.extra = kwargs
 
@@ -84,6 +87,7 @@ class Solver(object):
             particles, plan.rigid, plan.boundaries, dim=self.dim, kr=plan.kr,
             kf=plan.kf, fric_coeff=plan.fric_coeff, gx=plan.gx, gy=plan.gy,
             gz=plan.gz, planar=plan.planar, ks=self.ks,
+            list_cap=self.list_cap, skin_factor=self.skin_factor,
             radius_scale=radius_scale)
         self.integrator.set_scene(self.scene)
         self.plan = plan

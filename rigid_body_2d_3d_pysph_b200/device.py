@@ -563,10 +563,12 @@ class DeviceScene(object):
             msgs.append('a particle touches more than %d bodies' %
                         _lib.RBX_MAX_KEYS)
         if st & _lib.STATUS_HIST_OVERFLOW:
-            msgs.append('more than ks=%d simultaneous contacts on a particle'
-                        % self.ks)
+            msgs.append('more than ks=%d simultaneous contacts on a particle '
+                        '(pass a larger ks)' % self.ks)
         if st & _lib.STATUS_LIST_OVERFLOW:
-            msgs.append('per-particle neighbour list overflow')
+            msgs.append('per-particle neighbour list overflow (list_cap=%d; '
+                        'pass a larger list_cap or a smaller skin_factor)'
+                        % self.list_cap)
         if msgs and raise_on_error:
             raise _lib.RbxError('device status 0x%x: %s' %
                                 (st, '; '.join(msgs)))

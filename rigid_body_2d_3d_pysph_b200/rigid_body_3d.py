@@ -213,7 +213,15 @@ class RigidBody3DScheme(Scheme):
     def _set_inertia(self, pa):
         set_moment_of_inertia_and_its_inverse(pa)
 
+    # device_setup = True routes the boundary identification through the CUDA
+    # cell list (setup_device.py) instead of the host KD-tree evaluator
+    device_setup = False
+
     def _identify_boundary(self, pa):
+        if self.device_setup:
+            from .setup_device import identify_boundary
+            identify_boundary(pa, self.dim)
+            return
         add_boundary_identification_properties(pa)
         equations = get_boundary_identification_etvf_equations([pa.name],
                                                                [pa.name])

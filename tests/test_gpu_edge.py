@@ -167,3 +167,25 @@ def test_more_than_four_source_bodies_on_one_particle():
     tnb = int(o.total_no_bodies[0])
     seen = (o.contact_force_normal_wij.reshape(-1, tnb) > 0).sum(1)
     assert seen[:4].max() >= 5, seen[:4]
+
+
+def test_device_boundary_identification_equals_host():
+    """the device setup path gives the host evaluator's
+    is_boundary (exactly) and normals (to rounding) on a 3-D body + tank and
+    on a 2-D ring-shaped body."""
+    from rigid_body_2d_3d_pysph_b200.rigid_body_3d import RigidBody3DScheme
+    from rigid_body_2d_3d_pysph_b200.setup_device import identify_boundary
+    from tests.util import load_config
+    for name, dim in (('benchmark_5_3d', 3), ('stack_of_cylinders', 2)):
+        arrays, meta = load_config(name)
+        for pa in arrays[:2]:
+            host = get_particle_array(name=pa.name, x=pa.x, y=pa.y, z=pa.z,
+                                      h=pa.h, m=pa.m, rho=pa.rho)
+            dev = get_particle_array(name=pa.name, x=pa.x, y=pa.y, z=pa.z,
+                                     h=pa.h, m=pa.m, rho=pa.rho)
+            RigidBody3DScheme([pa.name], None, dim=dim)._identify_boundary(host)
+            identify_boundary(dev, dim)
+            assert np.array_equal(host.is_boundary, dev.is_boundary), \
+                (name, pa.name)
+            assert host.is_boundary.sum() > 0
+            assert np.abs(host.normal - dev.normal).max() < 1e-10
