@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RBX_VERSION 101 /* 0.1.1 */
+#define RBX_VERSION 200 /* 0.2.0 */
 
 typedef enum {
   RBX_OK = 0,
@@ -127,6 +127,14 @@ typedef struct {
    * rbx_contact_slots applies the exact neighbour predicate to every entry
    * with the current positions, so the pair set is independent of the skin. */
   int32_t *nbr_pos, *nbr_dem, *nbr_cnt;
+  /* The lists as rbx_contact_slots reads them, made from the raw ones on a
+   * rebuild: work item t <-> particle nbr_order[t], the particles of every
+   * window of 1024 ordered by descending list length (so that the lanes of a
+   * warp run lists of equal length); nbr_cnt_srt[t] entries in
+   * nbr_srt[list_cap][n_rigid] (column t), grouped by source body in
+   * ascending dem_id; an entry is the global index of the source particle,
+   * bit 31 set on the first entry of a source body.                        */
+  int32_t *nbr_order, *nbr_cnt_srt, *nbr_srt;
   /* per body */
   const double *total_mass, *izz, *spacing0; /* [n_bodies]               */
   double *xcm, *vcm, *ang_mom, *omega;       /* [3 n_bodies]             */

@@ -42,8 +42,8 @@ struct SlotAcc {
   int gmin;               // its global index (tie rule: lowest index)
 };
 
-#ifndef RBX_KPRE
-#define RBX_KPRE 2
+#ifndef RBX_KLD
+#define RBX_KLD 4
 #endif
 #ifndef RBX_KACC
 #define RBX_KACC 4
@@ -56,7 +56,7 @@ struct SlotAcc {
 #endif
 constexpr int kWarps = RBX_CHUNK / 32;
 constexpr int kBatch = 4;        // staged candidates per thread per iteration
-constexpr int kPre = RBX_KPRE;   // list entries in flight per thread in k_slots
+constexpr int kLd = RBX_KLD;     // list entries in flight per thread in k_slots
 
 __global__ void __launch_bounds__(RBX_CHUNK, RBX_NB_MINB)
 k_neighbours(RbxScene S, RbxCells C, RbxParams P, double reach) {
@@ -310,329 +310,391 @@ __global__ void k_list_clear(RbxScene S, double skin) {
   if (S.rebuild && S.xcm_ref && skin > 0.) *S.rebuild = 0u;
 }
 
-constexpr int kAcc = RBX_KACC;  // slots accumulated per pass over the list
-constexpr int kFields = 10; // ax ay az w1 bx by bz w2 rmin (pmin,gmin)
+// ---- lists as the pair kernel reads them ------------------------------------
+// On a rebuild, per window of kSortW consecutive particles: a stable counting
+// sort of the particles by descending list length (work item t <-> particle
+// nbr_order[t]), and every list rewritten into column t of nbr_srt with its
+// entries grouped by source body in ascending dem_id (stable inside a body),
+// bit 31 marking the first entry of a body.  k_slots then
+//   * runs warps whose 32 lists have (nearly) the same length -- in particle
+//     order the lengths range from 0 (interior) to 60+ (corners) inside one
+//     warp and 60 % of the lanes idle,
+//   * accumulates the sums of one source body in registers and knows a slot
+//     is complete when the next marked entry arrives: no key search, no
+//     shared-memory read-modify-write per pair.
+constexpr int kSortW = 1024;
+constexpr int kSortBins = 256;
+constexpr unsigned kRunBit = 0x80000000u;
+
+__global__ void __launch_bounds__(kSortW, 1)
+k_list_sort(RbxScene S) {
+  if (S.rebuild && *S.rebuild == 0u) return;      // lists still valid
+  __shared__ int cnt[kSortW / 32][kSortBins];
+  __shared__ int start[kSortBins];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int base = blockIdx.x * kSortW;
+  const int p = base + tid;
+  const bool valid = p < S.n_rigid;
+  const int len = valid ? S.nbr_cnt[p] : 0;
+  // bin 0 = threads past the end (sorted last), bin len + 1 otherwise
+  const int key = valid ? (len < kSortBins - 2 ? len : kSortBins - 2) + 1 : 0;
+  for (int i = tid; i < (kSortW / 32) * kSortBins; i += kSortW) (&cnt[0][0])[i] = 0;
+  __syncthreads();
+  const unsigned grp = __match_any_sync(0xffffffffu, key);
+  const int within = __popc(grp & ((1u << lane) - 1u));
+  if (within == 0) cnt[wid][key] = __popc(grp);
+  __syncthreads();
+  if (tid < kSortBins) {                // per bin: exclusive prefix over warps
+    int run = 0;
+#pragma unroll 4
+    for (int w2 = 0; w2 < kSortW / 32; w2++) {
+      const int c = cnt[w2][tid];
+      cnt[w2][tid] = run;
+      run += c;
+    }
+    start[tid] = run;
+  }
+  __syncthreads();
+  if (wid == 0) {                       // descending exclusive scan over bins
+    constexpr int per = kSortBins / 32;
+    int tot[per], s = 0;
+#pragma unroll
+    for (int j = 0; j < per; j++) { tot[j] = start[kSortBins - 1 - (per * lane + j)]; s += tot[j]; }
+    int inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += v;
+    }
+    int run = inc - s;
+#pragma unroll
+    for (int j = 0; j < per; j++) { start[kSortBins - 1 - (per * lane + j)] = run; run += tot[j]; }
+  }
+  __syncthreads();
+  if (!valid) return;
+  const int t = base + start[key] + cnt[wid][key] + within;
+  const size_t n = (size_t)S.n_rigid;
+  S.nbr_order[t] = p;
+  const int *rd = S.nbr_dem + p, *rp = S.nbr_pos + p;
+  int *out = S.nbr_srt + t;
+  int cur = 0, o = 0;
+  bool have = false;
+  while (o < len) {
+    int nk = 0x7fffffff;
+    bool found = false;
+    const int *c = rd;
+    for (int e = 0; e < len; e++, c += n) {
+      const int d = *c;
+      if ((!have || d > cur) && d <= nk) { nk = d; found = true; }
+    }
+    if (!found) break;
+    bool first = true;
+    c = rd;
+    const int *cp = rp;
+    for (int e = 0; e < len; e++, c += n, cp += n) {
+      if (*c == nk) {
+        const unsigned q = (unsigned)*cp;
+        out[(size_t)o * n] = (int)(first ? (q | kRunBit) : q);
+        first = false;
+        o++;
+      }
+    }
+    cur = nk;
+    have = true;
+  }
+  S.nbr_cnt_srt[t] = o;
+}
+
+constexpr int kAcc = RBX_KACC;  // completed slots parked in shared memory
+constexpr int kFields = 8;      // ax ay az w1 bx by bz (qmin, qfirst)
+constexpr int kOvf = 28;        // further slots parked in local memory
+
+// Per-particle state of the force law that outlives one batch of slots.
+struct SlotOut {
+  double cfx, cfy, cfz;   // contact force on the particle so far
+  int nout;               // history entries written
+  int ki;                 // diagnostic slots written
+  unsigned st;            // status bits
+  unsigned nactive;       // slots in contact
+};
+
+// The parked slots of one particle -> normals, distance, force law, history
+// (ascending dem_id by construction of the lists).  Deliberately not inlined:
+// it runs once per particle after the pair loop (and, for a particle touching
+// more bodies than there are parking slots, in the middle of it), and its
+// live ranges must not be added to those of the pair loop.
+__device__ __noinline__ void
+finalize_slots(const RbxScene *Sp, const RbxParams *Pp, const RbxDiag *Dp,
+               const double (*acc)[kFields][RBX_CHUNK], const double (*ovf)[kFields],
+               int nk, int p, int tid, SlotOut *out) {
+  const RbxScene &S = *Sp;
+  const RbxParams &P = *Pp;
+  const RbxDiag &D = *Dp;
+  const size_t n_rigid = (size_t)S.n_rigid;
+  const int body = S.body[p];
+  const double spacing0 = S.spacing0[body];
+  double cfx = out->cfx, cfy = out->cfy, cfz = out->cfz;
+  int nout = out->nout, ki = out->ki;
+  unsigned st = out->st, nactive = out->nactive;
+  for (int sl = 0; sl < nk; sl++) {
+    double a_ax, a_ay, a_az, a_w1, a_bx, a_by, a_bz;
+    int2 pg;
+    if (sl < kAcc) {
+      pg = reinterpret_cast<const int2 *>(&acc[sl][7][tid])[0];
+      a_ax = acc[sl][0][tid]; a_ay = acc[sl][1][tid]; a_az = acc[sl][2][tid];
+      a_w1 = acc[sl][3][tid];
+      a_bx = acc[sl][4][tid]; a_by = acc[sl][5][tid]; a_bz = acc[sl][6][tid];
+    } else {
+      const double *o = ovf[sl - kAcc];
+      pg = reinterpret_cast<const int2 *>(&o[7])[0];
+      a_ax = o[0]; a_ay = o[1]; a_az = o[2]; a_w1 = o[3];
+      a_bx = o[4]; a_by = o[5]; a_bz = o[6];
+    }
+    if (pg.y < 0) continue;        // nothing of this body is in range now
+    const int key = S.dem_id[pg.y];
+    const double a_w2 = a_w1;
+    // ComputeContactForceNormals.post_loop :705-723
+    double nx = 0., ny = 0., nz = 0.;
+    if (a_w1 > 1e-12) {
+      nx = a_ax / a_w1; ny = a_ay / a_w1; nz = a_az / a_w1;
+      const double magn = sqrt(nx * nx + ny * ny + nz * nz);
+      nx /= magn; ny /= magn; nz /= magn;
+    }
+    // ...DistanceAndClosestPoint.post_loop :829-836, with
+    // dist_tmp = sum (n.XIJ) tmp2 = n . sum XIJ tmp2
+    double dist = 0.;
+    if (a_w2 > 1e-12) dist = (nx * a_bx + ny * a_by + nz * a_bz) / a_w2;
+    const int gmin = pg.x;                 // global index (-1: none)
+
+    // ComputeContactForce.post_loop :906-1032
+    double ovl_out = 0., ft0 = 0., ft1 = 0., ft2 = 0.;
+    const double overlap = spacing0 - dist;
+    if (overlap > 0. && overlap != spacing0) {
+      double vxs = 0., vys = 0., vzs = 0.;
+      if (gmin >= 0) { vxs = S.u[gmin]; vys = S.v[gmin]; vzs = S.w[gmin]; }
+      // previous state of this slot
+      double dl0 = 0., dl1 = 0., dl2 = 0., fn0 = 0., fn1 = 0., fn2 = 0.;
+      for (int s2 = 0; s2 < S.ks; s2++) {
+        const int hk = S.hist_key_in[(size_t)s2 * n_rigid + p];
+        if (hk < 0) break;
+        if (hk == key) {
+          const size_t o = (size_t)s2 * n_rigid + p, pl = (size_t)S.ks * n_rigid;
+          dl0 = S.hist_dlt_in[o]; dl1 = S.hist_dlt_in[pl + o]; dl2 = S.hist_dlt_in[2 * pl + o];
+          fn0 = S.hist_fn_in[o]; fn1 = S.hist_fn_in[pl + o]; fn2 = S.hist_fn_in[2 * pl + o];
+          break;
+        }
+      }
+      const double md = S.m[p];
+      const double ud = S.u[p], vd = S.v[p], wd = S.w[p];
+      const double vij_x = ud - vxs, vij_y = vd - vys, vij_z = wd - vzs;
+      const double vn = vij_x * nx + vij_y * ny + vij_z * nz;
+      ovl_out = overlap;
+      const double tmp = P.kr * overlap;
+      double eta = 0.;
+      if (S.eta_mode == 1) eta = S.eta[S.eta_row[body] + key];       // :925
+      else if (S.eta_mode == 2) eta = S.eta[0];
+      eta = eta * sqrt(md / 2. * P.kr);                               // :926
+      const double fnx = (tmp - eta * vn) * nx;
+      const double fny = (tmp - eta * vn) * ny;
+      const double fnz = (tmp - eta * vn) * nz;
+      const double vij_magn = sqrt(vij_x * vij_x + vij_y * vij_y + vij_z * vij_z);
+      if (vij_magn < 1e-12) {
+        dl0 = dl1 = dl2 = 0.;   // fn (fn0..2) keeps its previous value: Q3
+      } else {
+        const double tx = vij_x - nx * vn, ty = vij_y - ny * vn, tz = vij_z - nz * vn;
+        const double ti_magn = sqrt(tx * tx + ty * ty + tz * tz);
+        double ti_x = 0., ti_y = 0., ti_z = 0.;
+        if (ti_magn > 1e-12) { ti_x = tx / ti_magn; ti_y = ty / ti_magn; ti_z = tz / ti_magn; }
+        const double sx_ = dl0 + vij_x * P.dt, sy_ = dl1 + vij_y * P.dt, sz_ = dl2 + vij_z * P.dt;
+        const double ddt = sx_ * ti_x + sy_ * ti_y + sz_ * ti_z;
+        dl0 = ddt * ti_x; dl1 = ddt * ti_y; dl2 = ddt * ti_z;
+        const double fsx = -P.kf * dl0, fsy = -P.kf * dl1, fsz = -P.kf * dl2;
+        const double ft_magn = sqrt(fsx * fsx + fsy * fsy + fsz * fsz);
+        const double fn_magn = sqrt(fnx * fnx + fny * fny + fnz * fnz);
+        const double ca = P.fric_coeff * fn_magn;
+        const double ft_star = (ft_magn < ca) ? ft_magn : ca;  // (b<a)?b:a, App. C-7
+        ft0 = -ft_star * ti_x; ft1 = -ft_star * ti_y; ft2 = -ft_star * ti_z;
+        const double mx = -ft0 / P.kf, my = -ft1 / P.kf, mz = -ft2 / P.kf;
+        const double lt = sqrt(mx * mx + my * my + mz * mz);
+        dl0 = mx / lt; dl1 = my / lt; dl2 = mz / lt;            // Q1, Q2 (0/0 = NaN)
+        fn0 = fnx; fn1 = fny; fn2 = fnz;
+      }
+      cfx += fn0 + ft0; cfy += fn1 + ft1; cfz += fn2 + ft2;      // :1030-1032
+      nactive++;
+      if (nout < S.ks) {
+        const size_t o = (size_t)nout * n_rigid + p, pl = (size_t)S.ks * n_rigid;
+        S.hist_key_out[o] = key;
+        S.hist_dlt_out[o] = dl0; S.hist_dlt_out[pl + o] = dl1; S.hist_dlt_out[2 * pl + o] = dl2;
+        S.hist_fn_out[o] = fn0; S.hist_fn_out[pl + o] = fn1; S.hist_fn_out[2 * pl + o] = fn2;
+        nout++;
+      } else {
+        st |= RBX_STATUS_HIST_OVERFLOW;
+      }
+    }
+    // (else: the slot is zeroed, :1014-1027 -- an absent sparse slot)
+    if (D.key) {
+      if (ki < RBX_MAX_KEYS) {
+        const size_t o = (size_t)ki * n_rigid + p;
+        D.key[o] = key;
+        if (D.closest) D.closest[o] = gmin;
+        if (D.nx) { D.nx[o] = nx; D.ny[o] = ny; D.nz[o] = nz; }
+        if (D.dist) D.dist[o] = dist;
+        if (D.overlap) D.overlap[o] = ovl_out;
+        if (D.ftx) { D.ftx[o] = ft0; D.fty[o] = ft1; D.ftz[o] = ft2; }
+      } else {
+        st |= RBX_STATUS_SLOT_OVERFLOW;
+      }
+    }
+    ki++;
+  }
+  out->cfx = cfx; out->cfy = cfy; out->cfz = cfz;
+  out->nout = nout; out->ki = ki; out->st = st; out->nactive = nactive;
+}
 
 template <int DIM, bool UNIFORM_H>
 __global__ void __launch_bounds__(RBX_CHUNK, RBX_SLOTS_MINB)
-k_slots(RbxScene S, RbxCells C, RbxParams P, RbxDiag D, double h_uniform) {
-  // slot accumulators: [slot][field][thread] -> conflict-free, no dynamic
-  // register indexing.  Field 9 packs (pmin, gmin) as two ints.
+k_slots(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
+        const __grid_constant__ RbxDiag D, double h_uniform) {
+  // parked slots: [slot][field][thread] -> conflict-free.  Field 7 packs
+  // (closest source, first source of the body) as two ints.
   __shared__ double acc[kAcc][kFields][RBX_CHUNK];
 
-  // flat decomposition: thread <-> rigid particle, full warps regardless of
-  // the body sizes (a body of 100 particles would leave a quarter of the
-  // lanes of a 128-thread chunk idle, and this kernel is latency bound per
-  // warp).  The per-body force/torque sum is done by k_bodies from fx,fy,fz.
+  // work item t <-> particle nbr_order[t] (k_list_sort): full warps of equal
+  // list length.  The per-body force/torque sum is done by k_bodies.
   const int tid = threadIdx.x, lane = tid & 31;
-  const int p = blockIdx.x * RBX_CHUNK + tid;
-  const bool valid = p < S.n_rigid;
-  const int body = valid ? S.body[p] : 0;
+  const int t = blockIdx.x * RBX_CHUNK + tid;
+  const bool valid = t < S.n_rigid;
   const size_t n_rigid = (size_t)S.n_rigid;
 
-  double fx = 0, fy = 0, fz = 0, px = 0, py = 0, pz = 0;
   unsigned nactive = 0, npairs = 0;
   if (valid) {
-    px = S.x[p]; py = S.y[p]; pz = S.z[p];
+    const int p = S.nbr_order[t];
+    const int nlist = S.nbr_cnt_srt[t];
+    const double px = S.x[p], py = S.y[p], pz = S.z[p];
     const double ph = S.h[p];
-    const double md = S.m[p], rhod = S.rho[p];
-    const double ud = S.u[p], vd = S.v[p], wd = S.w[p];
-    const double spacing0 = S.spacing0[body];
-    const int nlist = S.nbr_cnt[p];
-    const int* __restrict__ lpos = S.nbr_pos + p;
-    const int* __restrict__ ldem = S.nbr_dem + p;
-    fx = md * P.gx; fy = md * P.gy; fz = md * P.gz;  // BodyForce :122-125
-    unsigned st = 0u;
     const double hij_u = 0.5 * (ph + h_uniform);
-    const double rmin0 = 4. * spacing0;              // :765
-    const double vol = md / rhod;
+    const double rmin0 = 4. * S.spacing0[S.body[p]];  // :765
+    const double vol = S.m[p] / S.rho[p];
     const double rs2 = P.radius_scale * P.radius_scale;
     const double hi2 = rbx_h2(rs2, ph);
     const double hj2_u = rbx_h2(rs2, h_uniform);
 
-    int nout = 0, ki = 0;
-    // A particle touching more than kAcc bodies takes further rounds; the
-    // keys already served are remembered here (rare path, local memory).
-    int served[32];
-    int n_served = 0;
-    bool more = nlist > 0;
-    while (more) {
-      more = false;
-      // ---- one pass over the list: every entry's pair math runs once and
-      //      lands in the accumulator of its source body --------------------
-      int keys[kAcc];
-#pragma unroll
-      for (int k = 0; k < kAcc; k++) keys[k] = 0x7fffffff;
-      int nk = 0;
-      int last_key = -1, last_sl = -1;
-      bool overflow = false;       // some key did not fit this round
-      // software pipeline over the list, kPre entries per stage:
-      //   stage L: list loads (dem, global idx) for batch b + 2
-      //   stage G: position gathers             for batch b + 1
-      //   stage C: pair math + accumulation     for batch b
-      // so that the two dependent memory round trips (list -> gather) of
-      // later batches overlap the FP64 chain of the current one.
-      int ddL[kPre], qqL[kPre];            // loaded lists, batch b + 1 / b + 2
-      int ddG[kPre], qqG[kPre];            // batch whose gathers are in flight
-      double gx[kPre], gy[kPre], gz[kPre], gh[kPre];
-      // cursors into the two list planes, advanced by kPre entries per call
-      // (no 64-bit index multiply per load)
-      const int *cdem = ldem, *cpos = lpos;
-      auto load_lists = [&](int e0, int *dd_, int *qq_) {
-#pragma unroll
-        for (int k = 0; k < kPre; k++) {
-          const bool in = e0 + k < nlist;
-          dd_[k] = in ? cdem[(size_t)k * n_rigid] : -1;
-          qq_[k] = in ? cpos[(size_t)k * n_rigid] : 0;
-        }
-        cdem += (size_t)kPre * n_rigid;
-        cpos += (size_t)kPre * n_rigid;
-        if (n_served) {
-#pragma unroll
-          for (int k = 0; k < kPre; k++)
-            for (int j = 0; j < n_served; j++) if (served[j] == dd_[k]) dd_[k] = -1;
-        }
-      };
-      load_lists(0, ddG, qqG);
-#pragma unroll
-      for (int k = 0; k < kPre; k++) {
-        if (ddG[k] >= 0) {
-          gx[k] = S.x[qqG[k]]; gy[k] = S.y[qqG[k]]; gz[k] = S.z[qqG[k]];
-          if (!UNIFORM_H) gh[k] = S.h[qqG[k]];
-        }
+    // the slot being accumulated (registers)
+    double ax = 0., ay = 0., az = 0., w1 = 0.;     // sum XIJ*tmp1, sum tmp1*RIJ (:686-690)
+    double bx = 0., by = 0., bz = 0.;              // sum XIJ*tmp2             (:807)
+    double r2thr = rmin0 * rmin0;  // r2 of the closest source so far (:811-818)
+    int qmin = -1;           // its global index
+    int qfirst = -1;         // first list entry of this body (-1: no slot open)
+    bool touched = false;    // some entry passed the neighbour predicate
+    int nk = 0;              // slots parked in shared memory
+    SlotOut so;
+    so.cfx = so.cfy = so.cfz = 0.;
+    so.nout = 0; so.ki = 0; so.st = 0u; so.nactive = 0u;
+
+    // A finished slot is parked in shared memory; the ones past kAcc (a
+    // particle near more than kAcc bodies: corners) in local memory.
+    double ovf[kOvf][kFields];
+    auto park = [&]() {
+      if (nk < kAcc) {
+        acc[nk][0][tid] = ax; acc[nk][1][tid] = ay; acc[nk][2][tid] = az;
+        acc[nk][3][tid] = w1;
+        acc[nk][4][tid] = bx; acc[nk][5][tid] = by; acc[nk][6][tid] = bz;
+        reinterpret_cast<int2 *>(&acc[nk][7][tid])[0] = make_int2(qmin, touched ? qfirst : -1);
+        nk++;
+      } else if (nk < kAcc + kOvf) {
+        double *o = ovf[nk - kAcc];
+        o[0] = ax; o[1] = ay; o[2] = az; o[3] = w1; o[4] = bx; o[5] = by; o[6] = bz;
+        reinterpret_cast<int2 *>(&o[7])[0] = make_int2(qmin, touched ? qfirst : -1);
+        nk++;
+      } else {
+        so.st |= RBX_STATUS_SLOT_OVERFLOW;
       }
-      load_lists(kPre, ddL, qqL);
-      for (int e0 = 0; e0 < nlist; e0 += kPre) {
-        int dd[kPre], qq[kPre];
-        double sx[kPre], sy[kPre], sz[kPre], sh[kPre];
+    };
+
+    // software pipeline over the list: the list entry of e + 1 + kLd is being
+    // loaded (coalesced stream from HBM) and the position of source e + 1 is
+    // being gathered (L1/L2) while the pair math of entry e runs.
+    int ql[kLd];
+    const int *cl = S.nbr_srt + t;
 #pragma unroll
-        for (int k = 0; k < kPre; k++) {
-          dd[k] = ddG[k]; qq[k] = qqG[k];
-          sx[k] = gx[k]; sy[k] = gy[k]; sz[k] = gz[k]; sh[k] = gh[k];
-          ddG[k] = ddL[k]; qqG[k] = qqL[k];
-        }
+    for (int j = 0; j < kLd; j++) {
+      ql[j] = (1 + j < nlist) ? cl[(size_t)(1 + j) * n_rigid] : 0;
+    }
+    int qc = nlist > 0 ? cl[0] : 0;
+    cl += (size_t)(1 + kLd) * n_rigid;
+    double sx, sy, sz, sh = 0.;
+    {
+      const int qi = qc & 0x7fffffff;
+      sx = S.x[qi]; sy = S.y[qi]; sz = S.z[qi];
+      if (!UNIFORM_H) sh = S.h[qi];
+    }
+
+    // ---- pairs: every entry's pair math runs once and lands in the registers
+    //      of the open slot; a marked entry parks the slot ---------------------
+    {
+      for (int e0 = 0; e0 < nlist; e0++) {
+        // stage G for entry e0 + 1, stage L for entry e0 + 1 + kLd
+        const int qn = ql[0];
+        const int qni = qn & 0x7fffffff;
+        const double gx = S.x[qni], gy = S.y[qni], gz = S.z[qni];
+        double gh = 0.;
+        if (!UNIFORM_H) gh = S.h[qni];
 #pragma unroll
-        for (int k = 0; k < kPre; k++) {       // stage G for batch b + 1
-          if (ddG[k] >= 0) {
-            gx[k] = S.x[qqG[k]]; gy[k] = S.y[qqG[k]]; gz[k] = S.z[qqG[k]];
-            if (!UNIFORM_H) gh[k] = S.h[qqG[k]];
+        for (int j = 0; j + 1 < kLd; j++) ql[j] = ql[j + 1];
+        ql[kLd - 1] = (e0 + 1 + kLd < nlist) ? *cl : 0;
+        cl += n_rigid;
+        do {
+          const int qi = qc & 0x7fffffff;
+          if (qc < 0) {                        // first entry of a source body
+            if (qfirst >= 0) park();
+            ax = ay = az = w1 = bx = by = bz = 0.;
+            r2thr = rmin0 * rmin0; qmin = -1; qfirst = qi; touched = false;
           }
-        }
-        load_lists(e0 + 2 * kPre, ddL, qqL);   // stage L for batch b + 2
-#pragma unroll
-        for (int k = 0; k < kPre; k++) {
-          const int d = dd[k];
-          if (d < 0) continue;
-          const double x0 = px - sx[k], x1 = py - sy[k], x2 = pz - sz[k];
+          const double x0 = px - sx, x1 = py - sy, x2 = pz - sz;
           const double r2 = rbx_r2(x0, x1, x2);
           // exact neighbour predicate on the list entry:
           // the list was built with a skin, possibly several steps ago
-          if (!(r2 < hi2 || r2 < (UNIFORM_H ? hj2_u : rbx_h2(rs2, sh[k])))) continue;
-          if (n_served == 0) npairs++;
-          // slot of this key (first come, first served); entries come in
-          // runs of one source body, so try the previous entry's slot first
-          int sl = (d == last_key) ? last_sl : -1;
-          if (sl < 0) {
-#pragma unroll
-            for (int j = 0; j < kAcc; j++) if (keys[j] == d) sl = j;
-          }
-          if (sl < 0) {
-            if (nk < kAcc) {
-              sl = nk;
-#pragma unroll
-              for (int j = 0; j < kAcc; j++) if (j == nk) keys[j] = d;
-              nk++;
-#pragma unroll
-              for (int f = 0; f < 8; f++) acc[sl][f][tid] = 0.;
-              acc[sl][8][tid] = rmin0 * rmin0;   // r2 threshold for "closer"
-              reinterpret_cast<int2 *>(&acc[sl][9][tid])[0] = make_int2(-1, 0x7fffffff);
-            } else {
-              overflow = true;
-              continue;
-            }
-          }
+          if (!(r2 < hi2 || r2 < (UNIFORM_H ? hj2_u : rbx_h2(rs2, sh)))) break;
+          npairs++;
+          touched = true;
           // 1/r from rsqrt (1 ulp) instead of sqrt + division: the sums
           // below move by a few ulp (tolerance 1e-10), the dependent FP64
           // chain per entry is 3x shorter.  The closest-point decision, which
           // must match the CPU path bit for bit, still compares correctly
           // rounded sqrt values (below).
-          last_key = d; last_sl = sl;
           const double rinv = rsqrt(r2);
           const double rij = r2 * rinv;
-          const double hij = UNIFORM_H ? hij_u : 0.5 * (ph + sh[k]);
+          const double hij = UNIFORM_H ? hij_u : 0.5 * (ph + sh);
           const double wij = rbx_quintic<DIM>(rij, hij);
           const double tmp2 = vol * wij;                 // :803  m/rho * W
           const double tmp1 = tmp2 * rinv;               // :683  m/(rho r) * W
-          acc[sl][0][tid] += x0 * tmp1;                  // :686-688
-          acc[sl][1][tid] += x1 * tmp1;
-          acc[sl][2][tid] += x2 * tmp1;
-          acc[sl][3][tid] += tmp2;                       // :690  tmp1 * r
-          acc[sl][4][tid] += x0 * tmp2;                  // :807 (n . sum)
-          acc[sl][5][tid] += x1 * tmp2;
-          acc[sl][6][tid] += x2 * tmp2;
+          ax += x0 * tmp1; ay += x1 * tmp1; az += x2 * tmp1;   // :686-688
+          w1 += tmp2;                                    // :690  tmp1 * r
+          bx += x0 * tmp2; by += x1 * tmp2; bz += x2 * tmp2;   // :807 (n . sum)
           // :809: the second weight sum equals the first (tmp1*r == tmp2)
-          const double r2min = acc[sl][8][tid];
-          if (r2 <= r2min * (1. + 1e-14)) {              // :811 (+ tie rule Q6)
+          if (r2 <= r2thr * (1. + 1e-14)) {              // :811 (+ tie rule Q6)
             // possible new closest source: decide exactly as the reference
             // does, on correctly rounded distances
-            const int2 pg = reinterpret_cast<int2 *>(&acc[sl][9][tid])[0];
             const double rex = sqrt(r2);
-            const double rmin = (pg.x >= 0) ? sqrt(acc[sl][7][tid]) : rmin0;
+            const double rmin = (qmin >= 0) ? sqrt(r2thr) : rmin0;
             bool take = rex < rmin;
-            if (!take && pg.x >= 0 && rex == rmin)     // exact tie: lowest
-              take = qq[k] < pg.x;                     // global index wins
-            if (take) {
-              acc[sl][7][tid] = r2;                      // exact r2 of the best
-              acc[sl][8][tid] = r2;
-              reinterpret_cast<int2 *>(&acc[sl][9][tid])[0] = make_int2(qq[k], 0);
-            }
+            if (!take && qmin >= 0 && rex == rmin)     // exact tie: lowest
+              take = qi < qmin;                        // global index wins
+            if (take) { r2thr = r2; qmin = qi; }
           }
-        }
-      }
-      // ---- finalize this round's slots in ascending key order -------------
-      int ord[kAcc];
-#pragma unroll
-      for (int k = 0; k < kAcc; k++) ord[k] = k;
-#pragma unroll
-      for (int a2 = 0; a2 < kAcc - 1; a2++)
-#pragma unroll
-        for (int b2 = 0; b2 < kAcc - 1 - a2; b2++) {
-          const bool sw = keys[b2] > keys[b2 + 1];
-          const int k0 = sw ? keys[b2 + 1] : keys[b2], k1 = sw ? keys[b2] : keys[b2 + 1];
-          const int o0 = sw ? ord[b2 + 1] : ord[b2], o1 = sw ? ord[b2] : ord[b2 + 1];
-          keys[b2] = k0; keys[b2 + 1] = k1; ord[b2] = o0; ord[b2 + 1] = o1;
-        }
-      for (int kk = 0; kk < nk; kk++) {
-        int key = 0, sl = 0;
-#pragma unroll
-        for (int j = 0; j < kAcc; j++) if (j == kk) { key = keys[j]; sl = ord[j]; }
-        const double a_ax = acc[sl][0][tid], a_ay = acc[sl][1][tid], a_az = acc[sl][2][tid];
-        const double a_w1 = acc[sl][3][tid];
-        const double a_bx = acc[sl][4][tid], a_by = acc[sl][5][tid], a_bz = acc[sl][6][tid];
-        const double a_w2 = a_w1;
-        const int2 pg = reinterpret_cast<int2 *>(&acc[sl][9][tid])[0];
-        // ComputeContactForceNormals.post_loop :705-723
-        double nx = 0., ny = 0., nz = 0.;
-        if (a_w1 > 1e-12) {
-          nx = a_ax / a_w1; ny = a_ay / a_w1; nz = a_az / a_w1;
-          const double magn = sqrt(nx * nx + ny * ny + nz * nz);
-          nx /= magn; ny /= magn; nz /= magn;
-        }
-        // ...DistanceAndClosestPoint.post_loop :829-836, with
-        // dist_tmp = sum (n.XIJ) tmp2 = n . sum XIJ tmp2
-        double dist = 0.;
-        if (a_w2 > 1e-12) dist = (nx * a_bx + ny * a_by + nz * a_bz) / a_w2;
-        double vxs = 0., vys = 0., vzs = 0.;
-        const int gmin = pg.x;                 // global index (-1: none)
-        if (pg.x >= 0) { vxs = S.u[gmin]; vys = S.v[gmin]; vzs = S.w[gmin]; }
-
-        // previous state of this slot
-        double dl0 = 0., dl1 = 0., dl2 = 0., fn0 = 0., fn1 = 0., fn2 = 0.;
-        for (int s2 = 0; s2 < S.ks; s2++) {
-          const int hk = S.hist_key_in[(size_t)s2 * n_rigid + p];
-          if (hk < 0) break;
-          if (hk == key) {
-            const size_t o = (size_t)s2 * n_rigid + p, pl = (size_t)S.ks * n_rigid;
-            dl0 = S.hist_dlt_in[o]; dl1 = S.hist_dlt_in[pl + o]; dl2 = S.hist_dlt_in[2 * pl + o];
-            fn0 = S.hist_fn_in[o]; fn1 = S.hist_fn_in[pl + o]; fn2 = S.hist_fn_in[2 * pl + o];
-            break;
-          }
-        }
-
-        // ComputeContactForce.post_loop :906-1032
-        double ovl_out = 0., ft0 = 0., ft1 = 0., ft2 = 0.;
-        const double overlap = spacing0 - dist;
-        bool active = false;
-        if (overlap > 0. && overlap != spacing0) {
-          active = true;
-          const double vij_x = ud - vxs, vij_y = vd - vys, vij_z = wd - vzs;
-          const double vn = vij_x * nx + vij_y * ny + vij_z * nz;
-          ovl_out = overlap;
-          const double tmp = P.kr * overlap;
-          double eta = 0.;
-          if (S.eta_mode == 1) eta = S.eta[S.eta_row[body] + key];       // :925
-          else if (S.eta_mode == 2) eta = S.eta[0];
-          eta = eta * sqrt(md / 2. * P.kr);                               // :926
-          const double fnx = (tmp - eta * vn) * nx;
-          const double fny = (tmp - eta * vn) * ny;
-          const double fnz = (tmp - eta * vn) * nz;
-          const double vij_magn = sqrt(vij_x * vij_x + vij_y * vij_y + vij_z * vij_z);
-          if (vij_magn < 1e-12) {
-            dl0 = dl1 = dl2 = 0.;   // fn (fn0..2) keeps its previous value: Q3
-          } else {
-            const double tx = vij_x - nx * vn, ty = vij_y - ny * vn, tz = vij_z - nz * vn;
-            const double ti_magn = sqrt(tx * tx + ty * ty + tz * tz);
-            double ti_x = 0., ti_y = 0., ti_z = 0.;
-            if (ti_magn > 1e-12) { ti_x = tx / ti_magn; ti_y = ty / ti_magn; ti_z = tz / ti_magn; }
-            const double sx_ = dl0 + vij_x * P.dt, sy_ = dl1 + vij_y * P.dt, sz_ = dl2 + vij_z * P.dt;
-            const double ddt = sx_ * ti_x + sy_ * ti_y + sz_ * ti_z;
-            dl0 = ddt * ti_x; dl1 = ddt * ti_y; dl2 = ddt * ti_z;
-            const double fsx = -P.kf * dl0, fsy = -P.kf * dl1, fsz = -P.kf * dl2;
-            const double ft_magn = sqrt(fsx * fsx + fsy * fsy + fsz * fsz);
-            const double fn_magn = sqrt(fnx * fnx + fny * fny + fnz * fnz);
-            const double ca = P.fric_coeff * fn_magn;
-            const double ft_star = (ft_magn < ca) ? ft_magn : ca;  // (b<a)?b:a, App. C-7
-            ft0 = -ft_star * ti_x; ft1 = -ft_star * ti_y; ft2 = -ft_star * ti_z;
-            const double mx = -ft0 / P.kf, my = -ft1 / P.kf, mz = -ft2 / P.kf;
-            const double lt = sqrt(mx * mx + my * my + mz * mz);
-            dl0 = mx / lt; dl1 = my / lt; dl2 = mz / lt;            // Q1, Q2 (0/0 = NaN)
-            fn0 = fnx; fn1 = fny; fn2 = fnz;
-          }
-        } else {
-          dl0 = dl1 = dl2 = 0.; fn0 = fn1 = fn2 = 0.;
-        }
-        fx += fn0 + ft0; fy += fn1 + ft1; fz += fn2 + ft2;         // :1030-1032
-
-        if (active) {
-          nactive++;
-          if (nout < S.ks) {
-            const size_t o = (size_t)nout * n_rigid + p, pl = (size_t)S.ks * n_rigid;
-            S.hist_key_out[o] = key;
-            S.hist_dlt_out[o] = dl0; S.hist_dlt_out[pl + o] = dl1; S.hist_dlt_out[2 * pl + o] = dl2;
-            S.hist_fn_out[o] = fn0; S.hist_fn_out[pl + o] = fn1; S.hist_fn_out[2 * pl + o] = fn2;
-            nout++;
-          } else {
-            st |= RBX_STATUS_HIST_OVERFLOW;
-          }
-        }
-        if (D.key) {
-          if (ki < RBX_MAX_KEYS) {
-            const size_t o = (size_t)ki * n_rigid + p;
-            D.key[o] = key;
-            if (D.closest) D.closest[o] = gmin;
-            if (D.nx) { D.nx[o] = nx; D.ny[o] = ny; D.nz[o] = nz; }
-            if (D.dist) D.dist[o] = dist;
-            if (D.overlap) D.overlap[o] = ovl_out;
-            if (D.ftx) { D.ftx[o] = ft0; D.fty[o] = ft1; D.ftz[o] = ft2; }
-          } else {
-            st |= RBX_STATUS_SLOT_OVERFLOW;
-          }
-        }
-        ki++;
-      }
-      // more than kAcc bodies touch this particle: remember what was served
-      // and go over the list again for the rest (slots are then finalized in
-      // ascending dem_id per round, not globally: only the order in which
-      // their forces are added changes)
-      if (overflow) {
-        if (n_served + nk <= 32) {
-          for (int kk = 0; kk < nk; kk++) {
-            int key = 0;
-#pragma unroll
-            for (int j = 0; j < kAcc; j++) if (j == kk) key = keys[j];
-            served[n_served++] = key;
-          }
-          more = true;
-        } else {
-          st |= RBX_STATUS_SLOT_OVERFLOW;
-        }
+        } while (false);
+        qc = qn; sx = gx; sy = gy; sz = gz; sh = gh;
       }
     }
-    if (nout < S.ks) S.hist_key_out[(size_t)nout * n_rigid + p] = -1;
+    if (qfirst >= 0) park();
+    finalize_slots(&S, &P, &D, acc, ovf, nk, p, tid, &so);
+    nactive = so.nactive;
+    if (so.nout < S.ks) S.hist_key_out[(size_t)so.nout * n_rigid + p] = -1;
     if (D.key)
-      for (int k2 = ki; k2 < RBX_MAX_KEYS; k2++) D.key[(size_t)k2 * n_rigid + p] = -1;
-    if (st && S.status) atomicOr(S.status, st);
-    S.fx[p] = fx; S.fy[p] = fy; S.fz[p] = fz;
+      for (int k2 = so.ki; k2 < RBX_MAX_KEYS; k2++) D.key[(size_t)k2 * n_rigid + p] = -1;
+    if (so.st && S.status) atomicOr(S.status, so.st);
+    const double md = S.m[p];                        // BodyForce :122-125
+    S.fx[p] = md * P.gx + so.cfx; S.fy[p] = md * P.gy + so.cfy; S.fz[p] = md * P.gz + so.cfz;
   }
 
   if (S.counters) {
@@ -654,6 +716,7 @@ static int check_contact_args(const RbxScene *scene, const RbxCells *cells, cons
   if (scene->ks < 1 || (scene->dim != 2 && scene->dim != 3)) return RBX_ERR_INVALID;
   if (!(params->reach > 0.) || scene->list_cap < 1) return RBX_ERR_INVALID;
   if (!scene->nbr_pos || !scene->nbr_dem || !scene->nbr_cnt || !scene->counters) return RBX_ERR_INVALID;
+  if (!scene->nbr_srt || !scene->nbr_order || !scene->nbr_cnt_srt) return RBX_ERR_INVALID;
   return RBX_OK;
 }
 
@@ -669,6 +732,7 @@ extern "C" int rbx_contact_neighbours(const RbxScene *scene, const RbxCells *cel
     const int grid = nb < 148 * RBX_NB_MINB * 4 ? nb : 148 * RBX_NB_MINB * 4;
     k_neighbours<<<grid, RBX_CHUNK, 0, st>>>(*scene, *cells, *params, params->reach + params->skin);
   }
+  k_list_sort<<<rbx_blocks(scene->n_rigid, kSortW), kSortW, 0, st>>>(*scene);
   if (scene->rebuild)
     k_list_commit<<<rbx_blocks(scene->n_bodies, 256), 256, 0, st>>>(*scene);
   k_list_clear<<<1, 1, 0, st>>>(*scene, params->skin);
@@ -687,11 +751,11 @@ extern "C" int rbx_contact_slots(const RbxScene *scene, const RbxCells *cells,
   const bool uni = params->h_uniform > 0.;
   const int ng = rbx_blocks(scene->n_rigid, RBX_CHUNK);
   if (scene->dim == 3) {
-    if (uni) k_slots<3, true><<<ng, RBX_CHUNK, 0, st>>>(*scene, *cells, *params, d, params->h_uniform);
-    else k_slots<3, false><<<ng, RBX_CHUNK, 0, st>>>(*scene, *cells, *params, d, 0.);
+    if (uni) k_slots<3, true><<<ng, RBX_CHUNK, 0, st>>>(*scene, *params, d, params->h_uniform);
+    else k_slots<3, false><<<ng, RBX_CHUNK, 0, st>>>(*scene, *params, d, 0.);
   } else {
-    if (uni) k_slots<2, true><<<ng, RBX_CHUNK, 0, st>>>(*scene, *cells, *params, d, params->h_uniform);
-    else k_slots<2, false><<<ng, RBX_CHUNK, 0, st>>>(*scene, *cells, *params, d, 0.);
+    if (uni) k_slots<2, true><<<ng, RBX_CHUNK, 0, st>>>(*scene, *params, d, params->h_uniform);
+    else k_slots<2, false><<<ng, RBX_CHUNK, 0, st>>>(*scene, *params, d, 0.);
   }
   RBX_CHECK_LAUNCH();
   return RBX_OK;
