@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RBX_VERSION 200 /* 0.2.0 */
+#define RBX_VERSION 201 /* 0.2.1 */
 
 typedef enum {
   RBX_OK = 0,
@@ -120,20 +120,19 @@ typedef struct {
   const int32_t *chunk_start; /* [n_chunks + 1] particle ranges          */
   const int32_t *chunk_body;  /* [n_chunks]                              */
   const int32_t *body_chunk;  /* [n_bodies + 1] chunk ranges per body    */
-  /* Neighbour lists, [list_cap][n_rigid]: global index and dem_id of every
-   * gated source within reach + skin of the particle when the list was
-   * built; nbr_cnt[n_rigid] entries per particle.  Built by
-   * rbx_contact_neighbours when *rebuild != 0, reused otherwise;
-   * rbx_contact_slots applies the exact neighbour predicate to every entry
-   * with the current positions, so the pair set is independent of the skin. */
-  int32_t *nbr_pos, *nbr_dem, *nbr_cnt;
-  /* The lists as rbx_contact_slots reads them, made from the raw ones on a
-   * rebuild: work item t <-> particle nbr_order[t], the particles of every
-   * window of 1024 ordered by descending list length (so that the lanes of a
-   * warp run lists of equal length); nbr_cnt_srt[t] entries in
-   * nbr_srt[list_cap][n_rigid] (column t), grouped by source body in
-   * ascending dem_id; an entry is the global index of the source particle,
-   * bit 31 set on the first entry of a source body.                        */
+  /* Neighbour lists.  nbr_pos[list_cap][n_rigid] (column = particle): global
+   * index of every gated source within reach + skin of the particle when the
+   * list was built, the sources of one body contiguous, bit 31 set on the
+   * first entry of a body; nbr_cnt[n_rigid] entries per particle.  Built by
+   * rbx_contact_neighbours when *rebuild != 0, reused otherwise.
+   * rbx_contact_slots reads the transposed copy made at the same time:
+   * work item t <-> particle nbr_order[t], the particles of every window of
+   * 256 ordered by descending list length (so that the lanes of a warp run
+   * lists of equal length); nbr_cnt_srt[t] entries in column t of
+   * nbr_srt[list_cap][n_rigid], bit 31 set on the LAST entry of a body.  It
+   * applies the exact neighbour predicate to every entry with the current
+   * positions, so the pair set is independent of the skin.               */
+  int32_t *nbr_pos, *nbr_cnt;
   int32_t *nbr_order, *nbr_cnt_srt, *nbr_srt;
   /* per body */
   const double *total_mass, *izz, *spacing0; /* [n_bodies]               */

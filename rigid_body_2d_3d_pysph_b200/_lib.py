@@ -47,7 +47,7 @@ _SCENE_INTS = ['n_total', 'n_rigid', 'n_bodies', 'n_chunks', 'dim', 'ks',
 _SCENE_PTRS = ['x', 'y', 'z', 'u', 'v', 'w', 'h', 'm', 'rho', 'dem_id',
                'fx', 'fy', 'fz', 'dx0', 'dy0', 'dz0', 'body', 'is_boundary',
                'normal0', 'normal', 'chunk_start', 'chunk_body', 'body_chunk',
-               'nbr_pos', 'nbr_dem', 'nbr_cnt', 'nbr_order', 'nbr_cnt_srt',
+               'nbr_pos', 'nbr_cnt', 'nbr_order', 'nbr_cnt_srt',
                'nbr_srt', 'total_mass', 'izz', 'spacing0', 'xcm', 'vcm',
                'ang_mom', 'omega', 'force', 'torque', 'R', 'R_prev', 'iinv_b',
                'iinv_g', 'xcm0', 'vcm0', 'ang_mom0', 'R0', 'eta', 'eta_row',

@@ -51,12 +51,20 @@ struct SlotAcc {
 #ifndef RBX_NB_MINB
 #define RBX_NB_MINB 6
 #endif
+#ifndef RBX_SLOTS_CTA
+#define RBX_SLOTS_CTA 32
+#endif
 #ifndef RBX_SLOTS_MINB
-#define RBX_SLOTS_MINB 4
+#define RBX_SLOTS_MINB (512 / RBX_SLOTS_CTA)
 #endif
 constexpr int kWarps = RBX_CHUNK / 32;
 constexpr int kBatch = 4;        // staged candidates per thread per iteration
 constexpr int kLd = RBX_KLD;     // list entries in flight per thread in k_slots
+
+constexpr int kHash = RBX_CHUNK;                 // hash slots = group ids of a tile
+constexpr int kGIter = RBX_TILE / RBX_CHUNK;     // tile entries per thread
+constexpr int kEmptyKey = (int)0x80000000;       // never a dem_id
+constexpr unsigned kRunBit = 0x80000000u;
 
 __global__ void __launch_bounds__(RBX_CHUNK, RBX_NB_MINB)
 k_neighbours(RbxScene S, RbxCells C, RbxParams P, double reach) {
@@ -64,9 +72,15 @@ k_neighbours(RbxScene S, RbxCells C, RbxParams P, double reach) {
   // superset of the neighbour set; k_slots applies the exact predicate.
   if (S.rebuild && *S.rebuild == 0u) return;      // lists still valid
   // tile entry: position relative to the box centre in FP32 (x, y, z) and the
-  // global index of the source (w, as bits); dem_id beside it
+  // global index of the source (w, as bits); dem_id beside it.  r_*: in
+  // arrival (cell) order; t_*: the same entries grouped by dem_id.
+  __shared__ float4 r_f[RBX_TILE];
+  __shared__ int r_dem[RBX_TILE];
   __shared__ float4 t_f[RBX_TILE];
   __shared__ int t_dem[RBX_TILE];
+  __shared__ int h_key[kHash];
+  __shared__ int g_off[kWarps][kHash];
+  __shared__ int g_scan[kWarps];
   __shared__ double red[kWarps][6];
   __shared__ int wtot[2][kBatch][kWarps];
   __shared__ int row_s[RBX_CHUNK], row_off[RBX_CHUNK + 1];
@@ -74,6 +88,7 @@ k_neighbours(RbxScene S, RbxCells C, RbxParams P, double reach) {
   __shared__ int range[6];
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
   const RbxGridInfo gi = *C.info;
   const size_t n_rigid = (size_t)S.n_rigid;
   // persistent CTAs over the chunks (a skipped evaluation then costs one
@@ -138,6 +153,8 @@ k_neighbours(RbxScene S, RbxCells C, RbxParams P, double reach) {
   bool list_overflow = false;
   unsigned long long ncand = 0;
   const int cap = S.list_cap;
+  int *wp = S.nbr_pos + (valid ? p : 0);   // next list entry of this particle
+  int last_dem = kEmptyKey;                // dem_id of the previous entry
 
   // The list only has to be a SUPERSET of the neighbour set (k_slots applies
   // the exact FP64 predicate to every entry), so the candidate test runs in
@@ -156,19 +173,107 @@ k_neighbours(RbxScene S, RbxCells C, RbxParams P, double reach) {
   int tile_cnt = 0;
   int it = 0;
 
-  // ---- 3. list predicate against the staged tile ---------------------------
+  // ---- 3. a full tile: group it by source body, test it, append the hits ----
   auto phase_a = [&]() {
-    __syncthreads();  // tile complete
+    __syncthreads();  // raw tile complete
+    // (a) Entries of one source body become contiguous (stable inside a
+    // body), so that a particle's hits come out as one run per body and
+    // k_slots can sum a body in registers.  Group id = slot of the dem_id in
+    // a 128-entry hash table; a stable counting sort over (group, warp) with
+    // every warp owning a contiguous quarter of the tile.  Which slot a
+    // dem_id gets may vary from run to run; the order inside a body does
+    // not, and k_slots finalizes bodies in ascending dem_id.
+    h_key[tid] = kEmptyKey;
+#pragma unroll
+    for (int w2 = 0; w2 < kWarps; w2++) g_off[w2][tid] = 0;
+    __syncthreads();
+    const int L = ((tile_cnt + RBX_CHUNK - 1) / RBX_CHUNK) * 32;   // per warp
+    const int jb = wid * L;
+    int gk[kGIter];
+#pragma unroll
+    for (int k = 0; k < kGIter; k++) {
+      gk[k] = kHash + lane;               // absent entry: matches nobody
+      if (32 * k < L) {
+        const int j = jb + 32 * k + lane;
+        if (j < tile_cnt) {
+          const int d = r_dem[j];
+          unsigned h = ((unsigned)d * 2654435761u) >> 25;
+          for (int probe = 0; probe < kHash; probe++) {
+            const int old = atomicCAS(&h_key[h], kEmptyKey, d);
+            if (old == kEmptyKey || old == d) break;
+            h = (h + 1u) & (kHash - 1);
+          }
+          gk[k] = (int)h;
+        }
+        const unsigned grp = __match_any_sync(0xffffffffu, gk[k]);
+        if (gk[k] < kHash && (grp & lt_mask) == 0u) g_off[wid][gk[k]] += __popc(grp);
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    {                                      // counts -> first output position
+      int c[kWarps], tot = 0;
+#pragma unroll
+      for (int w2 = 0; w2 < kWarps; w2++) { c[w2] = g_off[w2][tid]; tot += c[w2]; }
+      int inc = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+      }
+      if (lane == 31) g_scan[wid] = inc;
+      __syncthreads();
+      int run = inc - tot;
+#pragma unroll
+      for (int w2 = 0; w2 < kWarps; w2++) if (w2 < wid) run += g_scan[w2];
+#pragma unroll
+      for (int w2 = 0; w2 < kWarps; w2++) { g_off[w2][tid] = run; run += c[w2]; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kGIter; k++) {
+      if (32 * k < L) {
+        const int j = jb + 32 * k + lane;
+        const bool in = gk[k] < kHash;
+        const unsigned grp = __match_any_sync(0xffffffffu, gk[k]);
+        const int within = __popc(grp & lt_mask);
+        const int base = in ? g_off[wid][gk[k]] : 0;
+        __syncwarp();
+        if (in && within == 0) g_off[wid][gk[k]] = base + __popc(grp);
+        __syncwarp();
+        if (in) {
+          t_f[base + within] = r_f[j];
+          t_dem[base + within] = r_dem[j];
+        }
+      }
+    }
+    __syncthreads();  // grouped tile complete
+    // (b) list predicate.  32 tile entries at a time: a branch-free pass
+    // collects the hits in a bit mask, a second loop appends them -- the
+    // append then runs once per hit of the busiest lane instead of once per
+    // tested entry in which any lane hits (4 in 5).  An entry is the global
+    // index of the source, bit 31 set when it starts a new source body.
     if (valid) {
       ncand += (unsigned long long)tile_cnt;
-#pragma unroll 4
-      for (int j = 0; j < tile_cnt; j++) {
-        const float4 f = t_f[j];
-        const float dxf = pfx - f.x, dyf = pfy - f.y, dzf = pfz - f.z;
-        if (fmaf(dzf, dzf, fmaf(dyf, dyf, dxf * dxf)) < thr_f) {
+      for (int j0 = 0; j0 < tile_cnt; j0 += 32) {
+        unsigned mask = 0u;
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          const float4 f = t_f[j0 + j];       // RBX_TILE is a multiple of 32
+          const float dxf = pfx - f.x, dyf = pfy - f.y, dzf = pfz - f.z;
+          if (fmaf(dzf, dzf, fmaf(dyf, dyf, dxf * dxf)) < thr_f) mask |= 1u << j;
+        }
+        const int left = tile_cnt - j0;
+        if (left < 32) mask &= (1u << left) - 1u;
+        while (mask) {
+          const int j = j0 + __ffs((int)mask) - 1;
+          mask &= mask - 1u;
           if (nlist < cap) {
-            S.nbr_pos[(size_t)nlist * n_rigid + p] = __float_as_int(f.w);
-            S.nbr_dem[(size_t)nlist * n_rigid + p] = t_dem[j];
+            const int d = t_dem[j];
+            const unsigned q = (unsigned)__float_as_int(t_f[j].w);
+            *wp = (int)(d != last_dem ? (q | kRunBit) : q);
+            wp += n_rigid;
+            last_dem = d;
             nlist++;
           } else {
             list_overflow = true;
@@ -176,7 +281,7 @@ k_neighbours(RbxScene S, RbxCells C, RbxParams P, double reach) {
         }
       }
     }
-    __syncthreads();  // tile may be overwritten
+    __syncthreads();  // tiles may be overwritten
     tile_cnt = 0;
   };
 
@@ -214,7 +319,6 @@ k_neighbours(RbxScene S, RbxCells C, RbxParams P, double reach) {
     const int total = row_off[RBX_CHUNK];
 
     for (int base = 0; base < total; base += kBatch * RBX_CHUNK) {
-      if (tile_cnt + kBatch * RBX_CHUNK > RBX_TILE) phase_a();
       bool keep[kBatch];
       double sx[kBatch], sy[kBatch], sz[kBatch];
       int sd[kBatch], sq[kBatch], sg[kBatch];
@@ -253,6 +357,12 @@ k_neighbours(RbxScene S, RbxCells C, RbxParams P, double reach) {
         if (lane == 0) wtot[buf][k][wid] = __popc(bal[k]);
       }
       __syncthreads();
+      int add = 0;
+#pragma unroll
+      for (int k = 0; k < kBatch; k++)
+#pragma unroll
+        for (int w2 = 0; w2 < kWarps; w2++) add += wtot[buf][k][w2];
+      if (tile_cnt + add > RBX_TILE) phase_a();   // uniform: the tile is full
       int run = tile_cnt;
 #pragma unroll
       for (int k = 0; k < kBatch; k++) {
@@ -264,10 +374,10 @@ k_neighbours(RbxScene S, RbxCells C, RbxParams P, double reach) {
           run += c;
         }
         if (keep[k]) {
-          const int dst = off + __popc(bal[k] & ((1u << lane) - 1u));
-          t_f[dst] = make_float4((float)(sx[k] - ccx), (float)(sy[k] - ccy),
+          const int dst = off + __popc(bal[k] & lt_mask);
+          r_f[dst] = make_float4((float)(sx[k] - ccx), (float)(sy[k] - ccy),
                                  (float)(sz[k] - ccz), __int_as_float(sg[k]));
-          t_dem[dst] = sd[k];
+          r_dem[dst] = sd[k];
         }
       }
       tile_cnt = run;
@@ -313,29 +423,36 @@ __global__ void k_list_clear(RbxScene S, double skin) {
 // ---- lists as the pair kernel reads them ------------------------------------
 // On a rebuild, per window of kSortW consecutive particles: a stable counting
 // sort of the particles by descending list length (work item t <-> particle
-// nbr_order[t]), and every list rewritten into column t of nbr_srt with its
-// entries grouped by source body in ascending dem_id (stable inside a body),
-// bit 31 marking the first entry of a body.  k_slots then
+// nbr_order[t]) and a transposition of the lists into that order (column t of
+// nbr_srt), through shared memory so that both the read and the write
+// coalesce.  The run marker moves from the first to the LAST entry of a
+// source body on the way.  k_slots then
 //   * runs warps whose 32 lists have (nearly) the same length -- in particle
 //     order the lengths range from 0 (interior) to 60+ (corners) inside one
 //     warp and 60 % of the lanes idle,
-//   * accumulates the sums of one source body in registers and knows a slot
-//     is complete when the next marked entry arrives: no key search, no
+//   * accumulates the sums of one source body in registers and parks the
+//     slot when the marked entry has been added: no key search, no
 //     shared-memory read-modify-write per pair.
-constexpr int kSortW = 1024;
+constexpr int kSortW = 256;       // particles per window = threads per CTA
 constexpr int kSortBins = 256;
-constexpr unsigned kRunBit = 0x80000000u;
+constexpr int kSortRows = 32;     // list rows staged in shared memory at a time
 
-__global__ void __launch_bounds__(kSortW, 1)
+__global__ void __launch_bounds__(kSortW, 4)
 k_list_sort(RbxScene S) {
   if (S.rebuild && *S.rebuild == 0u) return;      // lists still valid
+  __shared__ int stage[kSortRows + 1][kSortW];    // [row][particle of the window]
   __shared__ int cnt[kSortW / 32][kSortBins];
   __shared__ int start[kSortBins];
+  __shared__ int perm[kSortW];                    // sorted slot -> particle of the window
+  __shared__ int lens[kSortW];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int base = blockIdx.x * kSortW;
   const int p = base + tid;
   const bool valid = p < S.n_rigid;
   const int len = valid ? S.nbr_cnt[p] : 0;
+  const size_t n = (size_t)S.n_rigid;
+
+  // ---- 1. stable counting sort of the window by descending list length ------
   // bin 0 = threads past the end (sorted last), bin len + 1 otherwise
   const int key = valid ? (len < kSortBins - 2 ? len : kSortBins - 2) + 1 : 0;
   for (int i = tid; i < (kSortW / 32) * kSortBins; i += kSortW) (&cnt[0][0])[i] = 0;
@@ -346,7 +463,7 @@ k_list_sort(RbxScene S) {
   __syncthreads();
   if (tid < kSortBins) {                // per bin: exclusive prefix over warps
     int run = 0;
-#pragma unroll 4
+#pragma unroll
     for (int w2 = 0; w2 < kSortW / 32; w2++) {
       const int c = cnt[w2][tid];
       cnt[w2][tid] = run;
@@ -357,56 +474,66 @@ k_list_sort(RbxScene S) {
   __syncthreads();
   if (wid == 0) {                       // descending exclusive scan over bins
     constexpr int per = kSortBins / 32;
-    int tot[per], s = 0;
+    int tot[per], sum = 0;
 #pragma unroll
-    for (int j = 0; j < per; j++) { tot[j] = start[kSortBins - 1 - (per * lane + j)]; s += tot[j]; }
-    int inc = s;
+    for (int j = 0; j < per; j++) { tot[j] = start[kSortBins - 1 - (per * lane + j)]; sum += tot[j]; }
+    int inc = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int v = __shfl_up_sync(0xffffffffu, inc, o);
       if (lane >= o) inc += v;
     }
-    int run = inc - s;
+    int run = inc - sum;
 #pragma unroll
     for (int j = 0; j < per; j++) { start[kSortBins - 1 - (per * lane + j)] = run; run += tot[j]; }
   }
   __syncthreads();
-  if (!valid) return;
-  const int t = base + start[key] + cnt[wid][key] + within;
-  const size_t n = (size_t)S.n_rigid;
-  S.nbr_order[t] = p;
-  const int *rd = S.nbr_dem + p, *rp = S.nbr_pos + p;
-  int *out = S.nbr_srt + t;
-  int cur = 0, o = 0;
-  bool have = false;
-  while (o < len) {
-    int nk = 0x7fffffff;
-    bool found = false;
-    const int *c = rd;
-    for (int e = 0; e < len; e++, c += n) {
-      const int d = *c;
-      if ((!have || d > cur) && d <= nk) { nk = d; found = true; }
+  const int slot = start[key] + cnt[wid][key] + within;   // in [0, kSortW)
+  perm[slot] = tid;
+  lens[tid] = len;
+  if (valid) S.nbr_order[base + slot] = p;
+  int maxlen = len;                     // window maximum (strip loop bound)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
+  __syncthreads();                      // perm, lens complete; cnt is free
+  if (lane == 0) cnt[0][wid] = maxlen;
+  __syncthreads();
+  maxlen = 0;
+#pragma unroll
+  for (int w2 = 0; w2 < kSortW / 32; w2++) maxlen = max(maxlen, cnt[0][w2]);
+
+  // ---- 2. transpose, kSortRows list rows at a time (+ 1 row of lookahead) ----
+  const int src = perm[tid];            // the particle whose list this thread writes out
+  const int len_out = lens[src];
+  const int t = base + tid;             // ... into column t
+  const int *rp = S.nbr_pos + p;
+  for (int o0 = 0; o0 < maxlen; o0 += kSortRows) {
+    const int r_in = min(len - o0, kSortRows + 1);
+    {
+      const int *c = rp + (size_t)o0 * n;
+      for (int r = 0; r < r_in; r++, c += n) stage[r][tid] = *c;
     }
-    if (!found) break;
-    bool first = true;
-    c = rd;
-    const int *cp = rp;
-    for (int e = 0; e < len; e++, c += n, cp += n) {
-      if (*c == nk) {
-        const unsigned q = (unsigned)*cp;
-        out[(size_t)o * n] = (int)(first ? (q | kRunBit) : q);
-        first = false;
-        o++;
+    __syncthreads();
+    if (t < S.n_rigid) {
+      const int r1 = min(len_out - o0, kSortRows);
+      int *out = S.nbr_srt + (size_t)o0 * n + t;
+      int v = r1 > 0 ? stage[0][src] : 0;
+      for (int r = 0; r < r1; r++, out += n) {
+        // last entry of a source body <=> the next entry starts one
+        const bool more = o0 + r + 1 < len_out;
+        const int nv = more ? stage[r + 1][src] : -1;
+        *out = (int)(((unsigned)v & 0x7fffffffu) | (nv < 0 ? kRunBit : 0u));
+        v = nv;
       }
     }
-    cur = nk;
-    have = true;
+    __syncthreads();
   }
-  S.nbr_cnt_srt[t] = o;
+  if (t < S.n_rigid) S.nbr_cnt_srt[t] = len_out;
 }
 
+constexpr int kSlotsCta = RBX_SLOTS_CTA;   // threads per CTA of k_slots
 constexpr int kAcc = RBX_KACC;  // completed slots parked in shared memory
-constexpr int kFields = 8;      // ax ay az w1 bx by bz (qmin, qfirst)
+constexpr int kFields = 8;      // ax ay az w1 bx by bz (qmin, qany)
 constexpr int kOvf = 28;        // further slots parked in local memory
 
 // Per-particle state of the force law that outlives one batch of slots.
@@ -418,14 +545,15 @@ struct SlotOut {
   unsigned nactive;       // slots in contact
 };
 
-// The parked slots of one particle -> normals, distance, force law, history
-// (ascending dem_id by construction of the lists).  Deliberately not inlined:
-// it runs once per particle after the pair loop (and, for a particle touching
-// more bodies than there are parking slots, in the middle of it), and its
-// live ranges must not be added to those of the pair loop.
+// The parked slots of one particle -> normals, distance, force law, history,
+// in ascending dem_id.  A source body normally owns one slot; where its
+// entries were split over several runs of the list (a chunk whose candidates
+// did not fit one tile) the partial slots are added up here.  Deliberately
+// not inlined: it runs once per particle after the pair loop and its live
+// ranges must not be added to those of the loop.
 __device__ __noinline__ void
 finalize_slots(const RbxScene *Sp, const RbxParams *Pp, const RbxDiag *Dp,
-               const double (*acc)[kFields][RBX_CHUNK], const double (*ovf)[kFields],
+               double (*acc)[kFields][kSlotsCta], double (*ovf)[kFields],
                int nk, int p, int tid, SlotOut *out) {
   const RbxScene &S = *Sp;
   const RbxParams &P = *Pp;
@@ -436,23 +564,60 @@ finalize_slots(const RbxScene *Sp, const RbxParams *Pp, const RbxDiag *Dp,
   double cfx = out->cfx, cfy = out->cfy, cfz = out->cfz;
   int nout = out->nout, ki = out->ki;
   unsigned st = out->st, nactive = out->nactive;
+  auto ids = [&](int sl) -> int2 & {
+    return sl < kAcc ? reinterpret_cast<int2 *>(&acc[sl][7][tid])[0]
+                     : reinterpret_cast<int2 *>(&ovf[sl - kAcc][7])[0];
+  };
+  auto fld = [&](int sl, int f) -> double {
+    return sl < kAcc ? acc[sl][f][tid] : ovf[sl - kAcc][f];
+  };
+  // key of every slot: dem_id of one of its in-range sources (-1: none)
   for (int sl = 0; sl < nk; sl++) {
-    double a_ax, a_ay, a_az, a_w1, a_bx, a_by, a_bz;
-    int2 pg;
-    if (sl < kAcc) {
-      pg = reinterpret_cast<const int2 *>(&acc[sl][7][tid])[0];
-      a_ax = acc[sl][0][tid]; a_ay = acc[sl][1][tid]; a_az = acc[sl][2][tid];
-      a_w1 = acc[sl][3][tid];
-      a_bx = acc[sl][4][tid]; a_by = acc[sl][5][tid]; a_bz = acc[sl][6][tid];
-    } else {
-      const double *o = ovf[sl - kAcc];
-      pg = reinterpret_cast<const int2 *>(&o[7])[0];
-      a_ax = o[0]; a_ay = o[1]; a_az = o[2]; a_w1 = o[3];
-      a_bx = o[4]; a_by = o[5]; a_bz = o[6];
+    int2 &pg = ids(sl);
+    pg.y = pg.y >= 0 ? S.dem_id[pg.y] : -1;
+  }
+  int prev = -1;
+  for (;;) {
+    int key = 0x7fffffff;
+    for (int sl = 0; sl < nk; sl++) {
+      const int k2 = ids(sl).y;
+      if (k2 > prev && k2 < key) key = k2;
     }
-    if (pg.y < 0) continue;        // nothing of this body is in range now
-    const int key = S.dem_id[pg.y];
+    if (key == 0x7fffffff) break;
+    prev = key;
+    double a_ax = 0., a_ay = 0., a_az = 0., a_w1 = 0., a_bx = 0., a_by = 0., a_bz = 0.;
+    int gmin = -1;                       // closest source (global index, -1: none)
+    for (int sl = 0; sl < nk; sl++) {
+      const int2 pg = ids(sl);
+      if (pg.y != key) continue;
+      a_ax += fld(sl, 0); a_ay += fld(sl, 1); a_az += fld(sl, 2); a_w1 += fld(sl, 3);
+      a_bx += fld(sl, 4); a_by += fld(sl, 5); a_bz += fld(sl, 6);
+      if (pg.x >= 0) {
+        if (gmin < 0) {
+          gmin = pg.x;
+        } else {                         // two partial slots: the closer one
+          const double px = S.x[p], py = S.y[p], pz = S.z[p];
+          const double ra = sqrt(rbx_r2(px - S.x[gmin], py - S.y[gmin], pz - S.z[gmin]));
+          const double rb = sqrt(rbx_r2(px - S.x[pg.x], py - S.y[pg.x], pz - S.z[pg.x]));
+          if (rb < ra || (rb == ra && pg.x < gmin)) gmin = pg.x;
+        }
+      }
+    }
     const double a_w2 = a_w1;
+    // Quick reject.  dist = (n . B) / w with n = A / |A|, so the slot can be
+    // in contact (overlap = spacing0 - dist > 0) only if A.B < spacing0 |A| w;
+    // tested on squares with a 1e-9 margin (the exact path below rounds at
+    // 1e-15), it spares all but the few slots near contact the seven
+    // divisions and the square root.  A slot with w <= 1e-12 has n = 0,
+    // dist = 0, overlap == spacing0: inactive too.  Diagnostics want every
+    // slot's normal and distance and take the full path.
+    if (!D.key) {
+      if (!(a_w1 > 1e-12)) continue;
+      const double ab = a_ax * a_bx + a_ay * a_by + a_az * a_bz;
+      const double aa = a_ax * a_ax + a_ay * a_ay + a_az * a_az;
+      const double lim = spacing0 * a_w1;
+      if (ab > 0. && ab * ab > lim * lim * aa * (1. + 1e-9)) continue;
+    }
     // ComputeContactForceNormals.post_loop :705-723
     double nx = 0., ny = 0., nz = 0.;
     if (a_w1 > 1e-12) {
@@ -464,7 +629,6 @@ finalize_slots(const RbxScene *Sp, const RbxParams *Pp, const RbxDiag *Dp,
     // dist_tmp = sum (n.XIJ) tmp2 = n . sum XIJ tmp2
     double dist = 0.;
     if (a_w2 > 1e-12) dist = (nx * a_bx + ny * a_by + nz * a_bz) / a_w2;
-    const int gmin = pg.x;                 // global index (-1: none)
 
     // ComputeContactForce.post_loop :906-1032
     double ovl_out = 0., ft0 = 0., ft1 = 0., ft2 = 0.;
@@ -551,18 +715,28 @@ finalize_slots(const RbxScene *Sp, const RbxParams *Pp, const RbxDiag *Dp,
   out->nout = nout; out->ki = ki; out->st = st; out->nactive = nactive;
 }
 
+__device__ __noinline__ int
+park_overflow(double (*ovf)[kFields], int nk, double ax, double ay, double az, double w1,
+              double bx, double by, double bz, int2 ids, unsigned *st) {
+  if (nk >= kAcc + kOvf) { *st |= RBX_STATUS_SLOT_OVERFLOW; return nk; }
+  double *o = ovf[nk - kAcc];
+  o[0] = ax; o[1] = ay; o[2] = az; o[3] = w1; o[4] = bx; o[5] = by; o[6] = bz;
+  reinterpret_cast<int2 *>(&o[7])[0] = ids;
+  return nk + 1;
+}
+
 template <int DIM, bool UNIFORM_H>
-__global__ void __launch_bounds__(RBX_CHUNK, RBX_SLOTS_MINB)
+__global__ void __launch_bounds__(kSlotsCta, RBX_SLOTS_MINB)
 k_slots(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
         const __grid_constant__ RbxDiag D, double h_uniform) {
   // parked slots: [slot][field][thread] -> conflict-free.  Field 7 packs
-  // (closest source, first source of the body) as two ints.
-  __shared__ double acc[kAcc][kFields][RBX_CHUNK];
+  // (closest source, some in-range source of the body) as two ints.
+  __shared__ double acc[kAcc][kFields][kSlotsCta];
 
   // work item t <-> particle nbr_order[t] (k_list_sort): full warps of equal
   // list length.  The per-body force/torque sum is done by k_bodies.
   const int tid = threadIdx.x, lane = tid & 31;
-  const int t = blockIdx.x * RBX_CHUNK + tid;
+  const int t = blockIdx.x * kSlotsCta + tid;
   const bool valid = t < S.n_rigid;
   const size_t n_rigid = (size_t)S.n_rigid;
 
@@ -584,7 +758,6 @@ k_slots(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
     double bx = 0., by = 0., bz = 0.;              // sum XIJ*tmp2             (:807)
     double r2thr = rmin0 * rmin0;  // r2 of the closest source so far (:811-818)
     int qmin = -1;           // its global index
-    int qfirst = -1;         // first list entry of this body (-1: no slot open)
     bool touched = false;    // some entry passed the neighbour predicate
     int nk = 0;              // slots parked in shared memory
     SlotOut so;
@@ -594,46 +767,47 @@ k_slots(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
     // A finished slot is parked in shared memory; the ones past kAcc (a
     // particle near more than kAcc bodies: corners) in local memory.
     double ovf[kOvf][kFields];
-    auto park = [&]() {
+    auto park = [&](int2 ids) {
       if (nk < kAcc) {
         acc[nk][0][tid] = ax; acc[nk][1][tid] = ay; acc[nk][2][tid] = az;
         acc[nk][3][tid] = w1;
         acc[nk][4][tid] = bx; acc[nk][5][tid] = by; acc[nk][6][tid] = bz;
-        reinterpret_cast<int2 *>(&acc[nk][7][tid])[0] = make_int2(qmin, touched ? qfirst : -1);
-        nk++;
-      } else if (nk < kAcc + kOvf) {
-        double *o = ovf[nk - kAcc];
-        o[0] = ax; o[1] = ay; o[2] = az; o[3] = w1; o[4] = bx; o[5] = by; o[6] = bz;
-        reinterpret_cast<int2 *>(&o[7])[0] = make_int2(qmin, touched ? qfirst : -1);
+        reinterpret_cast<int2 *>(&acc[nk][7][tid])[0] = ids;
         nk++;
       } else {
-        so.st |= RBX_STATUS_SLOT_OVERFLOW;
+        nk = park_overflow(ovf, nk, ax, ay, az, w1, bx, by, bz, ids, &so.st);
       }
     };
 
-    // software pipeline over the list: the list entry of e + 1 + kLd is being
-    // loaded (coalesced stream from HBM) and the position of source e + 1 is
-    // being gathered (L1/L2) while the pair math of entry e runs.
+    // software pipeline over the list: the list entry of e + 2 + kLd is being
+    // loaded (coalesced stream from HBM) and the positions of sources e + 1
+    // and e + 2 are being gathered (L1/L2) while the pair math of entry e
+    // runs -- one iteration is about a hundred instructions, less than an L2
+    // round trip under load even with four warps per scheduler.
     int ql[kLd];
     const int *cl = S.nbr_srt + t;
 #pragma unroll
     for (int j = 0; j < kLd; j++) {
-      ql[j] = (1 + j < nlist) ? cl[(size_t)(1 + j) * n_rigid] : 0;
+      ql[j] = (2 + j < nlist) ? cl[(size_t)(2 + j) * n_rigid] : 0;
     }
     int qc = nlist > 0 ? cl[0] : 0;
-    cl += (size_t)(1 + kLd) * n_rigid;
-    double sx, sy, sz, sh = 0.;
+    int qa = nlist > 1 ? cl[n_rigid] : 0;
+    cl += (size_t)(2 + kLd) * n_rigid;
+    double sx, sy, sz, sh = 0., ax1, ay1, az1, ah1 = 0.;
     {
-      const int qi = qc & 0x7fffffff;
+      const int qi = qc & 0x7fffffff, qj = qa & 0x7fffffff;
       sx = S.x[qi]; sy = S.y[qi]; sz = S.z[qi];
       if (!UNIFORM_H) sh = S.h[qi];
+      ax1 = S.x[qj]; ay1 = S.y[qj]; az1 = S.z[qj];
+      if (!UNIFORM_H) ah1 = S.h[qj];
     }
 
     // ---- pairs: every entry's pair math runs once and lands in the registers
     //      of the open slot; a marked entry parks the slot ---------------------
     {
+#pragma unroll 3
       for (int e0 = 0; e0 < nlist; e0++) {
-        // stage G for entry e0 + 1, stage L for entry e0 + 1 + kLd
+        // stage G for entry e0 + 2, stage L for entry e0 + 2 + kLd
         const int qn = ql[0];
         const int qni = qn & 0x7fffffff;
         const double gx = S.x[qni], gy = S.y[qni], gz = S.z[qni];
@@ -641,27 +815,19 @@ k_slots(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
         if (!UNIFORM_H) gh = S.h[qni];
 #pragma unroll
         for (int j = 0; j + 1 < kLd; j++) ql[j] = ql[j + 1];
-        ql[kLd - 1] = (e0 + 1 + kLd < nlist) ? *cl : 0;
+        ql[kLd - 1] = (e0 + 2 + kLd < nlist) ? *cl : 0;
         cl += n_rigid;
-        do {
-          const int qi = qc & 0x7fffffff;
-          if (qc < 0) {                        // first entry of a source body
-            if (qfirst >= 0) park();
-            ax = ay = az = w1 = bx = by = bz = 0.;
-            r2thr = rmin0 * rmin0; qmin = -1; qfirst = qi; touched = false;
-          }
-          const double x0 = px - sx, x1 = py - sy, x2 = pz - sz;
-          const double r2 = rbx_r2(x0, x1, x2);
-          // exact neighbour predicate on the list entry:
-          // the list was built with a skin, possibly several steps ago
-          if (!(r2 < hi2 || r2 < (UNIFORM_H ? hj2_u : rbx_h2(rs2, sh)))) break;
+        const int qi = qc & 0x7fffffff;
+        const double x0 = px - sx, x1 = py - sy, x2 = pz - sz;
+        const double r2 = rbx_r2(x0, x1, x2);
+        // exact neighbour predicate on the list entry:
+        // the list was built with a skin, possibly several steps ago
+        if (r2 < hi2 || r2 < (UNIFORM_H ? hj2_u : rbx_h2(rs2, sh))) {
           npairs++;
           touched = true;
           // 1/r from rsqrt (1 ulp) instead of sqrt + division: the sums
           // below move by a few ulp (tolerance 1e-10), the dependent FP64
-          // chain per entry is 3x shorter.  The closest-point decision, which
-          // must match the CPU path bit for bit, still compares correctly
-          // rounded sqrt values (below).
+          // chain per entry is 3x shorter.
           const double rinv = rsqrt(r2);
           const double rij = r2 * rinv;
           const double hij = UNIFORM_H ? hij_u : 0.5 * (ph + sh);
@@ -672,21 +838,29 @@ k_slots(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
           w1 += tmp2;                                    // :690  tmp1 * r
           bx += x0 * tmp2; by += x1 * tmp2; bz += x2 * tmp2;   // :807 (n . sum)
           // :809: the second weight sum equals the first (tmp1*r == tmp2)
-          if (r2 <= r2thr * (1. + 1e-14)) {              // :811 (+ tie rule Q6)
-            // possible new closest source: decide exactly as the reference
-            // does, on correctly rounded distances
+          // :811 closest source (+ tie rule Q6).  The reference compares
+          // correctly rounded distances; a squared distance smaller by more
+          // than a few ulp decides the same way without the square roots,
+          // and only a near tie takes the exact path.
+          bool take = r2 < r2thr * (1. - 1e-14);
+          if (!take && r2 <= r2thr * (1. + 1e-14)) {
             const double rex = sqrt(r2);
             const double rmin = (qmin >= 0) ? sqrt(r2thr) : rmin0;
-            bool take = rex < rmin;
+            take = rex < rmin;
             if (!take && qmin >= 0 && rex == rmin)     // exact tie: lowest
               take = qi < qmin;                        // global index wins
-            if (take) { r2thr = r2; qmin = qi; }
           }
-        } while (false);
-        qc = qn; sx = gx; sy = gy; sz = gz; sh = gh;
+          if (take) { r2thr = r2; qmin = qi; }
+        }
+        if (qc < 0) {                  // last entry of this source body
+          park(make_int2(qmin, touched ? qi : -1));
+          ax = ay = az = w1 = bx = by = bz = 0.;
+          r2thr = rmin0 * rmin0; qmin = -1; touched = false;
+        }
+        qc = qa; sx = ax1; sy = ay1; sz = az1; sh = ah1;
+        qa = qn; ax1 = gx; ay1 = gy; az1 = gz; ah1 = gh;
       }
     }
-    if (qfirst >= 0) park();
     finalize_slots(&S, &P, &D, acc, ovf, nk, p, tid, &so);
     nactive = so.nactive;
     if (so.nout < S.ks) S.hist_key_out[(size_t)so.nout * n_rigid + p] = -1;
@@ -715,7 +889,7 @@ static int check_contact_args(const RbxScene *scene, const RbxCells *cells, cons
   if (!scene || !cells || !params) return RBX_ERR_INVALID;
   if (scene->ks < 1 || (scene->dim != 2 && scene->dim != 3)) return RBX_ERR_INVALID;
   if (!(params->reach > 0.) || scene->list_cap < 1) return RBX_ERR_INVALID;
-  if (!scene->nbr_pos || !scene->nbr_dem || !scene->nbr_cnt || !scene->counters) return RBX_ERR_INVALID;
+  if (!scene->nbr_pos || !scene->nbr_cnt || !scene->counters) return RBX_ERR_INVALID;
   if (!scene->nbr_srt || !scene->nbr_order || !scene->nbr_cnt_srt) return RBX_ERR_INVALID;
   return RBX_OK;
 }
@@ -749,13 +923,13 @@ extern "C" int rbx_contact_slots(const RbxScene *scene, const RbxCells *cells,
   RbxDiag d;
   if (diag) d = *diag; else memset(&d, 0, sizeof(d));
   const bool uni = params->h_uniform > 0.;
-  const int ng = rbx_blocks(scene->n_rigid, RBX_CHUNK);
+  const int ng = rbx_blocks(scene->n_rigid, kSlotsCta);
   if (scene->dim == 3) {
-    if (uni) k_slots<3, true><<<ng, RBX_CHUNK, 0, st>>>(*scene, *params, d, params->h_uniform);
-    else k_slots<3, false><<<ng, RBX_CHUNK, 0, st>>>(*scene, *params, d, 0.);
+    if (uni) k_slots<3, true><<<ng, kSlotsCta, 0, st>>>(*scene, *params, d, params->h_uniform);
+    else k_slots<3, false><<<ng, kSlotsCta, 0, st>>>(*scene, *params, d, 0.);
   } else {
-    if (uni) k_slots<2, true><<<ng, RBX_CHUNK, 0, st>>>(*scene, *params, d, params->h_uniform);
-    else k_slots<2, false><<<ng, RBX_CHUNK, 0, st>>>(*scene, *params, d, 0.);
+    if (uni) k_slots<2, true><<<ng, kSlotsCta, 0, st>>>(*scene, *params, d, params->h_uniform);
+    else k_slots<2, false><<<ng, kSlotsCta, 0, st>>>(*scene, *params, d, 0.);
   }
   RBX_CHECK_LAUNCH();
   return RBX_OK;

@@ -205,8 +205,6 @@ class DeviceScene(object):
         nr_ = max(self.n_rigid, 1)
         self.T['nbr_pos'] = torch.empty(self.list_cap * nr_, dtype=i32,
                                         device=dev)
-        self.T['nbr_dem'] = torch.empty(self.list_cap * nr_, dtype=i32,
-                                        device=dev)
         self.T['nbr_cnt'] = torch.zeros(nr_, dtype=i32, device=dev)
         # the same lists as the pair kernel reads them (length-ordered work
         # items, entries grouped by source body), made on every rebuild
@@ -312,7 +310,7 @@ class DeviceScene(object):
             s.normal = _ptr(P['normal'])
         s.list_cap = self.list_cap
         for n in ['chunk_start', 'chunk_body', 'body_chunk', 'nbr_pos',
-                  'nbr_dem', 'nbr_cnt', 'nbr_srt', 'nbr_order', 'nbr_cnt_srt',
+                  'nbr_cnt', 'nbr_srt', 'nbr_order', 'nbr_cnt_srt',
                   'eta', 'eta_row']:
             setattr(s, n, _ptr(T[n]))
         for n in ['total_mass', 'izz', 'spacing0', 'xcm', 'vcm', 'ang_mom',
