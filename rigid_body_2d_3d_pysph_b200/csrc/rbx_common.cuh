@@ -67,6 +67,39 @@ __device__ __forceinline__ double rbx_quintic(double rij, double h) {
   return val * fac;
 }
 
+// The same kernel without a branch (clamped terms are exact zeros, every
+// other operation is the one above): straight-line code that the scheduler
+// can interleave with a second, independent evaluation.
+template <int DIM>
+__device__ __forceinline__ double rbx_quintic_nb(double rij, double h) {
+  const double M_1_PI_ = 0.31830988618379067154;
+  const double h1 = 1. / h;
+  const double q = rij * h1;
+  double fac;
+  if (DIM == 2) fac = (M_1_PI_ * 7.0 / 478.0) * h1 * h1;
+  else if (DIM == 3) fac = (M_1_PI_ / 120.0) * h1 * h1 * h1;
+  else fac = (1.0 / 120.0) * h1;
+  const double t3 = q < 3. ? 3. - q : 0., t2 = q < 2. ? 2. - q : 0., t1 = q < 1. ? 1. - q : 0.;
+  const double a3 = t3 * t3, a2 = t2 * t2, a1 = t1 * t1;
+  double val = a3 * a3 * t3;
+  val -= 6.0 * (a2 * a2 * t2);
+  val += 15. * (a1 * a1 * t1);
+  return val * fac;
+}
+
+// 1/sqrt(x) without the special-case branch of the library routine:
+// MUFU.RSQ64H seed (2^-22) and two Newton steps (-> ~1e-16 relative).
+__device__ __forceinline__ double rbx_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    const double e = fma(-(x * y), y, 1.0);
+    y = fma(0.5 * y, e, y);
+  }
+  return y;
+}
+
 __device__ __forceinline__ int rbx_cell_coord(double x, double x0, double inv, int n) {
   int c = (int)floor((x - x0) * inv);
   return c < 0 ? 0 : (c >= n ? n - 1 : c);

@@ -54,6 +54,9 @@ struct SlotAcc {
 #ifndef RBX_SLOTS_CTA
 #define RBX_SLOTS_CTA 32
 #endif
+#ifndef RBX_SLOTS_WIDE
+#define RBX_SLOTS_WIDE 2
+#endif
 #ifndef RBX_SLOTS_MINB
 #define RBX_SLOTS_MINB (512 / RBX_SLOTS_CTA)
 #endif
@@ -779,6 +782,102 @@ k_slots(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
       }
     };
 
+#if RBX_SLOTS_WIDE == 2
+    // Two list entries per iteration.  Their pair math is independent
+    // straight-line code (no branch: a pair out of range has W = 0 and adds
+    // nothing -- the quintic spline's support is the neighbour radius -- so
+    // the predicate only gates the closest-point search), which doubles the
+    // instruction-level parallelism of what is otherwise one long dependent
+    // FP64 chain per entry; the sums are then added in list order.
+    // Software pipeline: entries e + 2 + j (j < kLd) are loaded (coalesced
+    // stream from HBM), the positions of sources e + 2, e + 3 are being
+    // gathered (L1/L2) while entries e, e + 1 are processed.
+    static_assert(kLd >= 2 && kLd % 2 == 0, "kLd");
+    int ql[kLd];
+    const int *cl = S.nbr_srt + t;
+#pragma unroll
+    for (int j = 0; j < kLd; j++) ql[j] = (2 + j < nlist) ? cl[(size_t)(2 + j) * n_rigid] : 0;
+    int qc0 = nlist > 0 ? cl[0] : 0;
+    int qc1 = nlist > 1 ? cl[n_rigid] : 0;
+    cl += (size_t)(2 + kLd) * n_rigid;
+    double c0x, c0y, c0z, c0h = 0., c1x, c1y, c1z, c1h = 0.;
+    {
+      const int qi = qc0 & 0x7fffffff, qj = qc1 & 0x7fffffff;
+      c0x = S.x[qi]; c0y = S.y[qi]; c0z = S.z[qi];
+      if (!UNIFORM_H) c0h = S.h[qi];
+      c1x = S.x[qj]; c1y = S.y[qj]; c1z = S.z[qj];
+      if (!UNIFORM_H) c1h = S.h[qj];
+    }
+    const double hmax2_u = fmax(hi2, hj2_u);
+    auto pair_math = [&](double sx, double sy, double sz, double sh, double &x0, double &x1,
+                         double &x2, double &r2, double &tmp1, double &tmp2, bool &in) {
+      x0 = px - sx; x1 = py - sy; x2 = pz - sz;
+      r2 = rbx_r2(x0, x1, x2);
+      // exact neighbour predicate on the list entry: the
+      // list was built with a skin, possibly several steps ago
+      in = UNIFORM_H ? (r2 < hmax2_u) : (r2 < hi2 || r2 < rbx_h2(rs2, sh));
+      // 1/r from rsqrt (1 ulp) instead of sqrt + division: the sums move by a
+      // few ulp (tolerance 1e-10), the dependent FP64 chain is 3x shorter
+      const double rinv = rbx_rsqrt(r2);
+      const double rij = r2 * rinv;
+      const double hij = UNIFORM_H ? hij_u : 0.5 * (ph + sh);
+      const double wij = rbx_quintic_nb<DIM>(rij, hij);
+      tmp2 = in ? vol * wij : 0.;                        // :803  m/rho * W
+      tmp1 = tmp2 * rinv;                                // :683  m/(rho r) * W
+    };
+    auto add_pair = [&](int qc, double x0, double x1, double x2, double r2, double tmp1,
+                        double tmp2, bool in) {
+      const int qi = qc & 0x7fffffff;
+      ax += x0 * tmp1; ay += x1 * tmp1; az += x2 * tmp1;     // :686-688
+      w1 += tmp2;                                      // :690  tmp1 * r
+      bx += x0 * tmp2; by += x1 * tmp2; bz += x2 * tmp2;     // :807 (n . sum)
+      // :809: the second weight sum equals the first (tmp1*r == tmp2)
+      if (in) {
+        npairs++;
+        touched = true;
+        // :811 closest source (+ tie rule Q6).  The reference compares
+        // correctly rounded distances; a squared distance smaller by more
+        // than a few ulp decides the same way without the square roots,
+        // and only a near tie takes the exact path.
+        bool take = r2 < r2thr * (1. - 1e-14);
+        if (!take && r2 <= r2thr * (1. + 1e-14)) {
+          const double rex = sqrt(r2);
+          const double rmin = (qmin >= 0) ? sqrt(r2thr) : rmin0;
+          take = rex < rmin;
+          if (!take && qmin >= 0 && rex == rmin)       // exact tie: lowest
+            take = qi < qmin;                          // global index wins
+        }
+        if (take) { r2thr = r2; qmin = qi; }
+      }
+      if (qc < 0) {                    // last entry of this source body
+        park(make_int2(qmin, touched ? qi : -1));
+        ax = ay = az = w1 = bx = by = bz = 0.;
+        r2thr = rmin0 * rmin0; qmin = -1; touched = false;
+      }
+    };
+    for (int e0 = 0; e0 < nlist; e0 += 2) {
+      // stage G for entries e0 + 2, e0 + 3; stage L for e0 + 2 + kLd, + 3 + kLd
+      const int qn0 = ql[0], qn1 = ql[1];
+      const int i0 = qn0 & 0x7fffffff, i1 = qn1 & 0x7fffffff;
+      const double g0x = S.x[i0], g0y = S.y[i0], g0z = S.z[i0];
+      const double g1x = S.x[i1], g1y = S.y[i1], g1z = S.z[i1];
+      double g0h = 0., g1h = 0.;
+      if (!UNIFORM_H) { g0h = S.h[i0]; g1h = S.h[i1]; }
+#pragma unroll
+      for (int j = 0; j + 2 < kLd; j++) ql[j] = ql[j + 2];
+      ql[kLd - 2] = (e0 + 2 + kLd < nlist) ? cl[0] : 0;
+      ql[kLd - 1] = (e0 + 3 + kLd < nlist) ? cl[n_rigid] : 0;
+      cl += 2 * n_rigid;
+      double a0, a1, a2, ar, at1, at2, b0, b1, b2, br, bt1, bt2;
+      bool ain, bin;
+      pair_math(c0x, c0y, c0z, c0h, a0, a1, a2, ar, at1, at2, ain);
+      pair_math(c1x, c1y, c1z, c1h, b0, b1, b2, br, bt1, bt2, bin);
+      add_pair(qc0, a0, a1, a2, ar, at1, at2, ain);
+      if (e0 + 1 < nlist) add_pair(qc1, b0, b1, b2, br, bt1, bt2, bin);
+      qc0 = qn0; c0x = g0x; c0y = g0y; c0z = g0z; c0h = g0h;
+      qc1 = qn1; c1x = g1x; c1y = g1y; c1z = g1z; c1h = g1h;
+    }
+#else
     // software pipeline over the list: the list entry of e + 2 + kLd is being
     // loaded (coalesced stream from HBM) and the positions of sources e + 1
     // and e + 2 are being gathered (L1/L2) while the pair math of entry e
@@ -861,6 +960,7 @@ k_slots(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
         qa = qn; ax1 = gx; ay1 = gy; az1 = gz; ah1 = gh;
       }
     }
+#endif
     finalize_slots(&S, &P, &D, acc, ovf, nk, p, tid, &so);
     nactive = so.nactive;
     if (so.nout < S.ks) S.hist_key_out[(size_t)so.nout * n_rigid + p] = -1;
