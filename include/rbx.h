@@ -123,7 +123,8 @@ typedef struct {
   /* Neighbour lists.  nbr_pos[list_cap][n_rigid] (column = particle): global
    * index of every gated source within reach + skin of the particle when the
    * list was built, the sources of one body contiguous, bit 31 set on the
-   * first entry of a body; nbr_cnt[n_rigid] entries per particle.  Built by
+   * first entry of a body; nbr_cnt[n_rigid] entries per particle (bit 30:
+   * a body may own more than one run of this list).  Built by
    * rbx_contact_neighbours when *rebuild != 0, reused otherwise.
    * rbx_contact_slots reads the transposed copy made at the same time:
    * work item t <-> particle nbr_order[t], the particles of every window of

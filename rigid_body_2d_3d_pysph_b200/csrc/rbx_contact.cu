@@ -68,6 +68,7 @@ constexpr int kHash = RBX_CHUNK;                 // hash slots = group ids of a 
 constexpr int kGIter = RBX_TILE / RBX_CHUNK;     // tile entries per thread
 constexpr int kEmptyKey = (int)0x80000000;       // never a dem_id
 constexpr unsigned kRunBit = 0x80000000u;
+constexpr int kSplitBit = 0x40000000;           // in nbr_cnt: bodies may be split
 
 __global__ void __launch_bounds__(RBX_CHUNK, RBX_NB_MINB)
 k_neighbours(RbxScene S, RbxCells C, RbxParams P, double reach) {
@@ -175,10 +176,12 @@ k_neighbours(RbxScene S, RbxCells C, RbxParams P, double reach) {
 
   int tile_cnt = 0;
   int it = 0;
+  int ntiles = 0;
 
   // ---- 3. a full tile: group it by source body, test it, append the hits ----
   auto phase_a = [&]() {
     __syncthreads();  // raw tile complete
+    if (tile_cnt > 0) ntiles++;
     // (a) Entries of one source body become contiguous (stable inside a
     // body), so that a particle's hits come out as one run per body and
     // k_slots can sum a body in registers.  Group id = slot of the dem_id in
@@ -390,7 +393,9 @@ k_neighbours(RbxScene S, RbxCells C, RbxParams P, double reach) {
   phase_a();
 
   if (valid) {
-    S.nbr_cnt[p] = nlist;
+    // bit 30: the chunk took more than one tile, a source body may own
+    // several runs of the list
+    S.nbr_cnt[p] = nlist | (ntiles > 1 ? kSplitBit : 0);
     if (list_overflow && S.status) atomicOr(S.status, RBX_STATUS_LIST_OVERFLOW);
   }
   // counters: candidate distance tests, list entries written
@@ -452,7 +457,8 @@ k_list_sort(RbxScene S) {
   const int base = blockIdx.x * kSortW;
   const int p = base + tid;
   const bool valid = p < S.n_rigid;
-  const int len = valid ? S.nbr_cnt[p] : 0;
+  const int len_raw = valid ? S.nbr_cnt[p] : 0;
+  const int len = len_raw & (kSplitBit - 1);
   const size_t n = (size_t)S.n_rigid;
 
   // ---- 1. stable counting sort of the window by descending list length ------
@@ -493,7 +499,7 @@ k_list_sort(RbxScene S) {
   __syncthreads();
   const int slot = start[key] + cnt[wid][key] + within;   // in [0, kSortW)
   perm[slot] = tid;
-  lens[tid] = len;
+  lens[tid] = len_raw;
   if (valid) S.nbr_order[base + slot] = p;
   int maxlen = len;                     // window maximum (strip loop bound)
 #pragma unroll
@@ -507,7 +513,8 @@ k_list_sort(RbxScene S) {
 
   // ---- 2. transpose, kSortRows list rows at a time (+ 1 row of lookahead) ----
   const int src = perm[tid];            // the particle whose list this thread writes out
-  const int len_out = lens[src];
+  const int len_out_raw = lens[src];
+  const int len_out = len_out_raw & (kSplitBit - 1);
   const int t = base + tid;             // ... into column t
   const int *rp = S.nbr_pos + p;
   for (int o0 = 0; o0 < maxlen; o0 += kSortRows) {
@@ -531,7 +538,7 @@ k_list_sort(RbxScene S) {
     }
     __syncthreads();
   }
-  if (t < S.n_rigid) S.nbr_cnt_srt[t] = len_out;
+  if (t < S.n_rigid) S.nbr_cnt_srt[t] = len_out_raw;
 }
 
 constexpr int kSlotsCta = RBX_SLOTS_CTA;   // threads per CTA of k_slots
@@ -557,7 +564,7 @@ struct SlotOut {
 __device__ __noinline__ void
 finalize_slots(const RbxScene *Sp, const RbxParams *Pp, const RbxDiag *Dp,
                double (*acc)[kFields][kSlotsCta], double (*ovf)[kFields],
-               int nk, int p, int tid, SlotOut *out) {
+               int nk, int p, int tid, bool split, SlotOut *out) {
   const RbxScene &S = *Sp;
   const RbxParams &P = *Pp;
   const RbxDiag &D = *Dp;
@@ -574,11 +581,30 @@ finalize_slots(const RbxScene *Sp, const RbxParams *Pp, const RbxDiag *Dp,
   auto fld = [&](int sl, int f) -> double {
     return sl < kAcc ? acc[sl][f][tid] : ovf[sl - kAcc][f];
   };
-  // key of every slot: dem_id of one of its in-range sources (-1: none)
+  // key of every slot: dem_id of one of its in-range sources (-1: none).
+  // Quick reject first: dist = (n . B) / w with n = A / |A|, so a slot can be
+  // in contact (overlap = spacing0 - dist > 0) only if A.B < spacing0 |A| w;
+  // tested on squares with a 1e-9 margin (the exact path rounds at 1e-15) it
+  // spares all but the few slots near contact everything that follows.  A
+  // slot with w <= 1e-12 has n = 0, dist = 0, overlap == spacing0: inactive
+  // too.  Not for split bodies (partial sums) and not for diagnostics, which
+  // want every slot's normal and distance.
+  const bool prefilter = !split && !D.key;
+  bool any = false;
   for (int sl = 0; sl < nk; sl++) {
     int2 &pg = ids(sl);
-    pg.y = pg.y >= 0 ? S.dem_id[pg.y] : -1;
+    int src = pg.y;
+    if (src >= 0 && prefilter) {
+      const double a0 = fld(sl, 0), a1 = fld(sl, 1), a2 = fld(sl, 2), w = fld(sl, 3);
+      const double ab = a0 * fld(sl, 4) + a1 * fld(sl, 5) + a2 * fld(sl, 6);
+      const double aa = a0 * a0 + a1 * a1 + a2 * a2;
+      const double lim = spacing0 * w;
+      if (!(w > 1e-12) || (ab > 0. && ab * ab > lim * lim * aa * (1. + 1e-9))) src = -1;
+    }
+    pg.y = src >= 0 ? S.dem_id[src] : -1;
+    any = any || src >= 0;
   }
+  if (!any) return;
   int prev = -1;
   for (;;) {
     int key = 0x7fffffff;
@@ -607,20 +633,6 @@ finalize_slots(const RbxScene *Sp, const RbxParams *Pp, const RbxDiag *Dp,
       }
     }
     const double a_w2 = a_w1;
-    // Quick reject.  dist = (n . B) / w with n = A / |A|, so the slot can be
-    // in contact (overlap = spacing0 - dist > 0) only if A.B < spacing0 |A| w;
-    // tested on squares with a 1e-9 margin (the exact path below rounds at
-    // 1e-15), it spares all but the few slots near contact the seven
-    // divisions and the square root.  A slot with w <= 1e-12 has n = 0,
-    // dist = 0, overlap == spacing0: inactive too.  Diagnostics want every
-    // slot's normal and distance and take the full path.
-    if (!D.key) {
-      if (!(a_w1 > 1e-12)) continue;
-      const double ab = a_ax * a_bx + a_ay * a_by + a_az * a_bz;
-      const double aa = a_ax * a_ax + a_ay * a_ay + a_az * a_az;
-      const double lim = spacing0 * a_w1;
-      if (ab > 0. && ab * ab > lim * lim * aa * (1. + 1e-9)) continue;
-    }
     // ComputeContactForceNormals.post_loop :705-723
     double nx = 0., ny = 0., nz = 0.;
     if (a_w1 > 1e-12) {
@@ -746,7 +758,8 @@ k_slots(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
   unsigned nactive = 0, npairs = 0;
   if (valid) {
     const int p = S.nbr_order[t];
-    const int nlist = S.nbr_cnt_srt[t];
+    const int cnt_raw = S.nbr_cnt_srt[t];
+    const int nlist = cnt_raw & (kSplitBit - 1);
     const double px = S.x[p], py = S.y[p], pz = S.z[p];
     const double ph = S.h[p];
     const double hij_u = 0.5 * (ph + h_uniform);
@@ -961,7 +974,7 @@ k_slots(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
       }
     }
 #endif
-    finalize_slots(&S, &P, &D, acc, ovf, nk, p, tid, &so);
+    finalize_slots(&S, &P, &D, acc, ovf, nk, p, tid, (cnt_raw & kSplitBit) != 0, &so);
     nactive = so.nactive;
     if (so.nout < S.ks) S.hist_key_out[(size_t)so.nout * n_rigid + p] = -1;
     if (D.key)

@@ -30,5 +30,5 @@ for i in range(8):
     ev[1].record()
     torch.cuda.synchronize()
     t3.append(ev[0].elapsed_time(ev[1]))
-cnt = sc.T['nbr_cnt'].float()
+cnt = (sc.T['nbr_cnt'] & 0x3fffffff).float()
 print('%s skin=%.2f cells %.3f ms  K1 %.3f ms  K2 %.3f ms  skipped(cells+K1) %.3f ms  list mean %.1f max %d' % (sys.argv[3] if len(sys.argv)>3 else '', skin, np.mean(t0[2:]), np.mean(t1[2:]), np.mean(t2[2:]), np.mean(t3[2:]), cnt.mean().item(), int(cnt.max().item())))
