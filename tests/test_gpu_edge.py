@@ -169,6 +169,29 @@ def test_more_than_four_source_bodies_on_one_particle():
     assert seen[:4].max() >= 5, seen[:4]
 
 
+def test_split_source_bodies_and_long_lists():
+    """h = 6 dx: one chunk sees more gated sources (18 wall rows + a second
+    body) than a shared-memory tile of k_neighbours holds, so a source body
+    is spread over several runs of the neighbour lists (bit 30 of nbr_cnt)
+    and k_slots has to add the partial slots up; the lists are also far
+    longer than one strip of the transposition."""
+    dx = 0.05
+    b1 = _block2d(8, 8, dx, 0.0, 0.0)
+    b2 = _block2d(5, 5, dx, 8 * dx + 0.95 * dx, 0.0)
+    i, j = np.meshgrid(np.arange(-20, 34), np.arange(18), indexing='ij')
+    wall = (i.ravel() * dx, -0.97 * dx - j.ravel() * dx, np.zeros(i.size))
+    # spacing0 = 8 dx: the kernel-weighted distance to an 18-row wall is
+    # several dx, the contact law must still see an overlap
+    arrays, s = _make(2, [b1, b2], wall, h_body=6 * dx, h_wall=6 * dx,
+                      spacing=8 * dx)
+    sc, g, o = _run_both(arrays, s, 2, 1e-5, 12, list_cap=1200)
+    cnt = sc.T['nbr_cnt'].cpu().numpy()
+    assert ((cnt >> 30) & 1).any(), 'no chunk needed a second tile'
+    assert (cnt & 0x3fffffff).max() > 500
+    assert np.abs(o.fy).max() > 3 * o.m[0] * 9.81    # in contact
+    assert sc.read_counters()['active_slots'] > 0
+
+
 def test_device_boundary_identification_equals_host():
     """the device setup path gives the host evaluator's
     is_boundary (exactly) and normals (to rounding) on a 3-D body + tank and
