@@ -760,6 +760,9 @@ k_slots(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
     const int p = S.nbr_order[t];
     const int cnt_raw = S.nbr_cnt_srt[t];
     const int nlist = cnt_raw & (kSplitBit - 1);
+    // partial slots of a split body and the slots of a diagnostics run are
+    // all parked; otherwise only those that pass the contact prefilter
+    const bool park_all = (cnt_raw & kSplitBit) != 0 || D.key != nullptr;
     const double px = S.x[p], py = S.y[p], pz = S.z[p];
     const double ph = S.h[p];
     const double hij_u = 0.5 * (ph + h_uniform);
@@ -863,7 +866,16 @@ k_slots(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
         if (take) { r2thr = r2; qmin = qi; }
       }
       if (qc < 0) {                    // last entry of this source body
-        park(make_int2(qmin, touched ? qi : -1));
+        // Contact prefilter on the finished sums (see finalize_slots): all
+        // but the few slots near contact end here, in registers.
+        bool keep = touched;
+        if (keep && !park_all) {
+          const double ab = ax * bx + ay * by + az * bz;
+          const double aa = ax * ax + ay * ay + az * az;
+          const double lim = (0.25 * rmin0) * w1;      // spacing0 * w
+          keep = w1 > 1e-12 && !(ab > 0. && ab * ab > lim * lim * aa * (1. + 1e-9));
+        }
+        if (keep || park_all) park(make_int2(qmin, touched ? qi : -1));
         ax = ay = az = w1 = bx = by = bz = 0.;
         r2thr = rmin0 * rmin0; qmin = -1; touched = false;
       }
@@ -974,7 +986,7 @@ k_slots(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
       }
     }
 #endif
-    finalize_slots(&S, &P, &D, acc, ovf, nk, p, tid, (cnt_raw & kSplitBit) != 0, &so);
+    if (nk > 0) finalize_slots(&S, &P, &D, acc, ovf, nk, p, tid, (cnt_raw & kSplitBit) != 0, &so);
     nactive = so.nactive;
     if (so.nout < S.ks) S.hist_key_out[(size_t)so.nout * n_rigid + p] = -1;
     if (D.key)
