@@ -121,19 +121,33 @@ __device__ __forceinline__ void drift_body(const RbxScene &S, int b, double dt) 
   rotate_body(S.R + i9, S.R + i9, om, dt, S.iinv_b + i9, S.planar ? nullptr : S.iinv_g + i9);
 }
 
-// mode bits: 1 = reduce chunk partials, 2 = kick, 4 = drift, 8 = kick before drift
+// mode bits: 1 = reduce, 2 = kick, 4 = drift, 8 = kick before drift
 // order executed: [reduce] [kick (post)] [kick (pre)] [drift]
+// The reduction wants a warp per body (lanes stride over its particles); the
+// 3x3 algebra of kick and drift (a few hundred dependent FP64 instructions
+// with divisions and square roots) is one thread's work -- with the reduce
+// bit clear the launch is a thread per body, 32 bodies per warp instead of
+// one warp idling 31 lanes per body.
 __global__ void k_bodies(RbxScene S, int mode, double dt, double skin) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+  if (!(mode & 1)) {
+    if (gt >= S.n_bodies) return;
+    if (mode & 2) kick_body(S, gt, dt / 2.);
+    if (mode & 8) kick_body(S, gt, dt / 2.);
+    if (mode & 4) { drift_body(S, gt, dt); check_displacement(S, gt, skin); }
+    return;
+  }
+  const int warp = gt >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= S.n_bodies) return;
   const int b = warp;
-  if (mode & 1) {
+  {
     // SumUpExternalForces.reduce :158-175: lanes stride over the body's
     // particles (contiguous), fixed shuffle tree => deterministic
     double v6[6] = {0, 0, 0, 0, 0, 0};
     const int q0 = S.chunk_start[S.body_chunk[b]], q1 = S.chunk_start[S.body_chunk[b + 1]];
     const double cx = S.xcm[3 * b], cy = S.xcm[3 * b + 1], cz = S.xcm[3 * b + 2];
+#pragma unroll 4
     for (int q = q0 + lane; q < q1; q += 32) {
       const double fx = S.fx[q], fy = S.fy[q], fz = S.fz[q];
       const double dx = S.x[q] - cx, dy = S.y[q] - cy, dz = S.z[q] - cz;
@@ -239,7 +253,8 @@ __global__ void k_pose(RbxScene S, int flags) {
 int launch_bodies(const RbxScene *S, int mode, double dt, double skin, cudaStream_t st) {
   if (S->n_bodies <= 0) return RBX_OK;
   const int T = 128;
-  k_bodies<<<rbx_blocks((long long)S->n_bodies * 32, T), T, 0, st>>>(*S, mode, dt, skin);
+  const long long threads = (mode & 1) ? (long long)S->n_bodies * 32 : S->n_bodies;
+  k_bodies<<<rbx_blocks(threads, T), T, 0, st>>>(*S, mode, dt, skin);
   RBX_CHECK_LAUNCH();
   return RBX_OK;
 }

@@ -88,16 +88,13 @@ __device__ __forceinline__ double rbx_quintic_nb(double rij, double h) {
 }
 
 // 1/sqrt(x) without the special-case branch of the library routine:
-// MUFU.RSQ64H seed (2^-22) and two Newton steps (-> ~1e-16 relative).
+// MUFU.RSQ64H seed (2^-22) and one third-order step y += y e (1/2 + 3/8 e),
+// e = 1 - x y^2 (-> 1e-16 relative), the library's own refinement.
 __device__ __forceinline__ double rbx_rsqrt(double x) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-#pragma unroll
-  for (int i = 0; i < 2; i++) {
-    const double e = fma(-(x * y), y, 1.0);
-    y = fma(0.5 * y, e, y);
-  }
-  return y;
+  const double e = fma(-x, y * y, 1.0);
+  return fma(fma(e, 0.375, 0.5), y * e, y);
 }
 
 __device__ __forceinline__ int rbx_cell_coord(double x, double x0, double inv, int n) {

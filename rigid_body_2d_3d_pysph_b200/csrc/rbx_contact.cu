@@ -880,6 +880,7 @@ k_slots(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
         r2thr = rmin0 * rmin0; qmin = -1; touched = false;
       }
     };
+#pragma unroll 2
     for (int e0 = 0; e0 < nlist; e0 += 2) {
       // stage G for entries e0 + 2, e0 + 3; stage L for e0 + 2 + kLd, + 3 + kLd
       const int qn0 = ql[0], qn1 = ql[1];
