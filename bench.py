@@ -293,24 +293,39 @@ def main():
                                           active_per_step, sc.n_bodies)
     peak, peak_src = peaks()
     traffic = None
+    limiter = None
     try:
         with open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')) as f:
             tr = json.load(f)
         if tr['config']['bodies'] == args.bodies:
-            traffic = tr['contact_dram_bytes_per_evaluation']
+            # DRAM bytes of an average evaluation: k_slots every time, the
+            # rebuild kernels on the share of evaluations that rebuild
+            share = 0. if contact_rebuild_ms <= contact_ms else \
+                (contact_ms - min(kms[1:])) / max(
+                    contact_rebuild_ms - min(kms[1:]), 1e-9)
+            traffic = tr['contact_dram_bytes_per_evaluation'] + \
+                share * tr['contact_dram_bytes_per_rebuild']
+            limiter = '; '.join(
+                '%s: %.0f %% FP64 pipe, %.0f %% issue active, %.1f of 32 '
+                'lanes, %d registers' % (
+                    n.split(' ')[0], k['fp64_pipe_pct'],
+                    k['issue_active_pct'], k['threads_per_inst'],
+                    k['registers'])
+                for n, k in tr['kernels'].items())
     except Exception:
         pass
     roof = {'bound': 'hbm',
             'kernel': 'contact evaluation (rbx_contact_mofidi): k_slots, plus '
-            'k_neighbours on the steps that rebuild the neighbour lists',
+            'k_neighbours + k_list_sort on the steps that rebuild the '
+            'neighbour lists',
             'achieved': contact_b / (contact_ms * 1e-3) / 1e9, 'peak': peak,
             'unit': 'GB/s', 'peak_source': peak_src, 'traffic': traffic,
             'traffic_source': 'profiles/r01_traffic.json (ncu dram__bytes '
-            'read+write of both launches)' if traffic else None,
-            'secondary_limiter': 'latency (k_slots: 25 % FP64 pipe, 46 % issue '
-            'active, 16 warps/SM at 128 registers) and FP64 issue '
-            '(k_neighbours: 36 % FP64 pipe, 63 % issue active): see '
-            'profiles/',
+            'read+write per launch, rebuild kernels weighted by the share of '
+            'evaluations that rebuild)' if traffic else None,
+            'secondary_limiter': ('FP64 issue and latency, not HBM (ncu, '
+                                  'profiles/r01_traffic.json): ' + limiter)
+            if limiter else None,
             'ms_per_launch': contact_ms,
             'ms_per_launch_with_list_rebuild': contact_rebuild_ms,
             'algorithmic_bytes_per_launch': contact_b}
@@ -388,8 +403,8 @@ def main():
                    min(args.settle, args.cpu_settle), args.cpu_steps)}
 
     if rank == 0:
-        launches_per_step = 16   # bodies, pose, 8 cell-list kernels,
-        #                          k_neighbours, list commit + clear,
+        launches_per_step = 17   # bodies, pose, 8 cell-list kernels,
+        #                          k_neighbours, k_list_sort, list commit + clear,
         #                          k_slots, bodies, pose (memsets not
         #                          counted; the cell-list kernels and
         #                          k_neighbours return at once on steps
