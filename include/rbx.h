@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RBX_VERSION 201 /* 0.2.1 */
+#define RBX_VERSION 202 /* 0.2.2 */
 
 typedef enum {
   RBX_OK = 0,
@@ -275,6 +275,15 @@ int rbx_gtvf_drift(const RbxScene *scene, double dt, double skin,
 #define RBX_POSE_VEL_PREV 4  /* velocities use R_prev (stage1 fused after drift) */
 #define RBX_POSE_NORMALS 8   /* rotate normal0 -> normal where is_boundary */
 int rbx_pose_particles(const RbxScene *scene, int flags, void *stream);
+
+/* Multi-GPU halo payload (no counterpart in the reference, which is single
+ * process): rows of 8 doubles {x, y, z, u, v, w, h, dem_id}.  pack gathers
+ * the particles index[0..n) into rows[n][8]; unpack writes rows[n][8] into
+ * the particles [first, first + n) (a static source array of the scene).   */
+int rbx_halo_pack(const RbxScene *scene, const int64_t *index, int32_t n,
+                  double *rows, void *stream);
+int rbx_halo_unpack(const RbxScene *scene, int32_t first, int32_t n,
+                    const double *rows, void *stream);
 
 /* RK2RigidBody3DStep (rigid_body_3d.py:406-575): stage 0 = py_initialize
  * (fix_q7 != 0 saves ang_mom0 of every body), 1 and 2 =

@@ -92,7 +92,8 @@ SYMBOLS = ['rbx_version', 'rbx_strerror', 'rbx_sizeof',
            'rbx_cells_workspace_bytes', 'rbx_cells_build', 'rbx_pairs_dump',
            'rbx_contact_mofidi', 'rbx_contact_neighbours',
            'rbx_contact_slots', 'rbx_reduce_bodies', 'rbx_gtvf_kick',
-           'rbx_gtvf_drift', 'rbx_pose_particles', 'rbx_rk2_stage',
+           'rbx_gtvf_drift', 'rbx_pose_particles', 'rbx_halo_pack',
+           'rbx_halo_unpack', 'rbx_rk2_stage',
            'rbx_gtvf_step', 'rbx_contact_lvc', 'rbx_dem_step',
            'rbx_boundary_identify']
 
@@ -139,6 +140,8 @@ def load():
     L.rbx_gtvf_kick.argtypes = [P(RbxScene), c_f64, c_vp]
     L.rbx_gtvf_drift.argtypes = [P(RbxScene), c_f64, c_f64, c_vp]
     L.rbx_pose_particles.argtypes = [P(RbxScene), ctypes.c_int, c_vp]
+    L.rbx_halo_pack.argtypes = [P(RbxScene), c_vp, c_i32, c_vp, c_vp]
+    L.rbx_halo_unpack.argtypes = [P(RbxScene), c_i32, c_i32, c_vp, c_vp]
     L.rbx_rk2_stage.argtypes = [P(RbxScene), ctypes.c_int, c_f64,
                                 ctypes.c_int, c_f64, c_vp]
     L.rbx_gtvf_step.argtypes = [P(RbxScene), P(RbxPoints), P(RbxCells),

@@ -250,6 +250,25 @@ __global__ void k_pose(RbxScene S, int flags) {
   }
 }
 
+// halo payload rows {x, y, z, u, v, w, h, dem_id}: thread <-> (particle, column)
+__global__ void k_halo_pack(RbxScene S, const int64_t *index, int n, double *rows) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n * 8) return;
+  const int c = k & 7;
+  const long long q = index[k >> 3];
+  const double *col[7] = {S.x, S.y, S.z, S.u, S.v, S.w, S.h};
+  rows[k] = c < 7 ? col[c][q] : (double)S.dem_id[q];
+}
+__global__ void k_halo_unpack(RbxScene S, int first, int n, const double *rows) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n * 8) return;
+  const int c = k & 7;
+  const int q = first + (k >> 3);
+  double *col[7] = {S.x, S.y, S.z, S.u, S.v, S.w, const_cast<double *>(S.h)};
+  if (c < 7) col[c][q] = rows[k];
+  else const_cast<int32_t *>(S.dem_id)[q] = (int32_t)rows[k];
+}
+
 int launch_bodies(const RbxScene *S, int mode, double dt, double skin, cudaStream_t st) {
   if (S->n_bodies <= 0) return RBX_OK;
   const int T = 128;
@@ -281,6 +300,25 @@ extern "C" int rbx_pose_particles(const RbxScene *scene, int flags, void *stream
   if (scene->n_rigid <= 0) return RBX_OK;
   if ((flags & RBX_POSE_VEL_PREV) && !scene->R_prev) return RBX_ERR_INVALID;
   k_pose<<<rbx_blocks(scene->n_rigid, 256), 256, 0, (cudaStream_t)stream>>>(*scene, flags);
+  RBX_CHECK_LAUNCH();
+  return RBX_OK;
+}
+
+extern "C" int rbx_halo_pack(const RbxScene *scene, const int64_t *index, int32_t n,
+                             double *rows, void *stream) {
+  if (!scene || n < 0 || (n > 0 && (!index || !rows))) return RBX_ERR_INVALID;
+  if (n == 0) return RBX_OK;
+  k_halo_pack<<<rbx_blocks((long long)n * 8, 256), 256, 0, (cudaStream_t)stream>>>(*scene, index, n, rows);
+  RBX_CHECK_LAUNCH();
+  return RBX_OK;
+}
+
+extern "C" int rbx_halo_unpack(const RbxScene *scene, int32_t first, int32_t n,
+                               const double *rows, void *stream) {
+  if (!scene || n < 0 || first < 0 || (long long)first + n > scene->n_total ||
+      (n > 0 && !rows)) return RBX_ERR_INVALID;
+  if (n == 0) return RBX_OK;
+  k_halo_unpack<<<rbx_blocks((long long)n * 8, 256), 256, 0, (cudaStream_t)stream>>>(*scene, first, n, rows);
   RBX_CHECK_LAUNCH();
   return RBX_OK;
 }

@@ -105,9 +105,17 @@ class SlabScene(object):
         assert int(src.numel()) == self.n_src_static + self.halo_cap, \
             'halo array must be last and fully source-flagged'
         self.own_src = src[src < scene.n_rigid]
+        # own sources per body: particles are grouped by body and own_src is
+        # ascending, so a body's sources are one contiguous range of own_src
+        nb = scene.n_bodies
+        cnt = torch.bincount(scene.P['body'][self.own_src].long(),
+                             minlength=max(nb, 1))
+        self.src_count = cnt
+        self.src_start = torch.cumsum(cnt, 0) - cnt
         self.n_halo = 0
         self._send_idx = None
         self._send_counts = self._recv_counts = None
+        self._send_buf = self._recv_buf = None
         self.bytes_sent = 0
         self.bytes_recv = 0
         self._set_source_count(0)
@@ -150,20 +158,37 @@ class SlabScene(object):
         lo_own = float(ivh[self.rank, 0]) + pad
         hi_own = float(ivh[self.rank, 1]) - pad
         idx = self.own_src
-        xs = P['x'][idx]
         rows = []
-        empty = torch.zeros(0, dtype=torch.int64, device=xs.device)
+        dev = idx.device
+        empty = torch.zeros(0, dtype=torch.int64, device=dev)
+        nb = sc.n_bodies
+        xc = sc.B['xcm'][0:3 * nb:3]
+        rb = sc.B['rmax'][:nb]
         for q in range(self.world):
             lo_q, hi_q = float(ivh[q, 0]), float(ivh[q, 1])
             if q == self.rank or hi_q < lo_own or lo_q > hi_own:
                 rows.append(empty)
                 continue
-            rows.append(torch.nonzero((xs >= lo_q) & (xs <= hi_q)).flatten())
+            # bodies that can reach into q's interval, then only their
+            # sources are tested (a few per cent of the slab): the same set,
+            # in the same ascending order, as testing every own source
+            bsel = torch.nonzero((xc + rb >= lo_q) &
+                                 (xc - rb <= hi_q)).flatten()
+            cnt = self.src_count[bsel]
+            first = self.src_start[bsel]
+            rep = torch.repeat_interleave(
+                torch.arange(bsel.numel(), device=dev), cnt)
+            off = torch.cumsum(cnt, 0) - cnt
+            pos = first[rep] + (torch.arange(rep.numel(), device=dev) -
+                                off[rep])
+            xs = P['x'][idx[pos]]
+            rows.append(pos[torch.nonzero((xs >= lo_q) &
+                                          (xs <= hi_q)).flatten()])
         gsel = idx[torch.cat(rows)]
         cols = self._pack(gsel)
         # rows of `cols` per destination are consecutive blocks
         offs = np.cumsum([0] + [r.numel() for r in rows])
-        rel = [torch.arange(int(offs[q]), int(offs[q + 1]), device=xs.device)
+        rel = [torch.arange(int(offs[q]), int(offs[q + 1]), device=dev)
                for q in range(self.world)]
         if self.world > 1:
             got, ns, nr, table = exchange_rows(cols, rel, self.rank,
@@ -197,27 +222,40 @@ class SlabScene(object):
         P['dem_id'][o:o + nr] = got[:, 7].to(torch.int32)
 
     def _refresh_halo(self):
-        cols = self._pack(self._send_idx)
-        dev = cols.device
-        send = list(torch.split(cols, self._send_counts, 0))
-        recv = [torch.empty(n, HALO_COLS, dtype=cols.dtype, device=dev)
-                for n in self._recv_counts]
+        """Same particles, same halo slots: one gather kernel, point-to-point
+        payload between slab neighbours, one scatter kernel."""
+        import ctypes
+        sc = self.sc
+        ns, nr = sum(self._send_counts), sum(self._recv_counts)
+        dev = sc.device
+        if self._send_buf is None or self._send_buf.shape[0] != ns:
+            self._send_buf = torch.empty(ns, HALO_COLS, dtype=torch.float64,
+                                         device=dev)
+        if self._recv_buf is None or self._recv_buf.shape[0] != nr:
+            self._recv_buf = torch.empty(nr, HALO_COLS, dtype=torch.float64,
+                                         device=dev)
+        if ns:
+            _lib.check(sc.lib.rbx_halo_pack(
+                ctypes.byref(sc.scene), self._send_idx.data_ptr(), ns,
+                self._send_buf.data_ptr(), sc.stream), 'rbx_halo_pack')
+        send = torch.split(self._send_buf, self._send_counts, 0)
+        recv = torch.split(self._recv_buf, self._recv_counts, 0)
         ops = []
         for q in range(self.world):
             if q == self.rank:
                 continue
             if self._send_counts[q] > 0:
-                ops.append(dist.P2POp(dist.isend, send[q].contiguous(), q,
-                                      self.group))
+                ops.append(dist.P2POp(dist.isend, send[q], q, self.group))
             if self._recv_counts[q] > 0:
                 ops.append(dist.P2POp(dist.irecv, recv[q], q, self.group))
         if ops:
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
-        nr = sum(self._recv_counts)
         if nr:
-            self._unpack(torch.cat(recv, 0), nr)
-        self.bytes_sent += sum(self._send_counts) * HALO_COLS * 8
+            _lib.check(sc.lib.rbx_halo_unpack(
+                ctypes.byref(sc.scene), self.halo_off, nr,
+                self._recv_buf.data_ptr(), sc.stream), 'rbx_halo_unpack')
+        self.bytes_sent += ns * HALO_COLS * 8
         self.bytes_recv += nr * HALO_COLS * 8
 
     def gtvf_step(self, dt, nsteps=1):
@@ -225,7 +263,7 @@ class SlabScene(object):
         re-pose (stage 2) and the force evaluation."""
         sc = self.sc
         sc.push_touched()
-        for _ in range(nsteps):
+        for k in range(nsteps):
             sc.gtvf_kick(dt)
             sc.gtvf_drift(dt)
             sc.pose(_lib.POSE_POS | _lib.POSE_VEL | _lib.POSE_VEL_PREV |
@@ -235,6 +273,11 @@ class SlabScene(object):
             sc.contact(dt)
             sc.reduce_bodies()
             sc.gtvf_kick(dt)
-            sc.pose(_lib.POSE_VEL)
+            # the stage-3 particle velocities of a step are overwritten by
+            # stage 1 of the next one before anything reads them (the halo
+            # payload is packed after stage 1): only the last step of a
+            # batch writes them, as in DeviceScene.gtvf_step
+            if k == nsteps - 1:
+                sc.pose(_lib.POSE_VEL)
         sc.steps_done += nsteps
         sc.mark_device_newer()
