@@ -6,28 +6,33 @@
 //   BodyForce.initialize                        rigid_body_common.py:115-125
 //   ComputeContactForce.post_loop               rigid_body_common.py:839-1032
 //
-// Two launches over the same decomposition: one CTA per "chunk" (<= 128
-// consecutive particles of one rigid body, thread t <-> particle p0 + t).
+// Three kernels.
 //
-// k_neighbours (issue bound; shared-memory staged; only on list rebuilds)
+// k_neighbours (instruction-issue bound; only on list rebuilds): persistent
+//   CTAs, one "chunk" at a time (<= 128 consecutive particles of one rigid
+//   body, thread t <-> particle p0 + t)
 //   1. reduces the chunk's bounding box,
 //   2. streams the cell-list rows overlapping box +- reach (coalesced SoA
 //      loads, 4 independent loads per thread per barrier), drops the body's
 //      own particles and everything outside the box, and compacts the rest
 //      into a shared-memory tile (deterministic ballot/prefix compaction),
-//   3. every thread tests its particle against the tile (broadcast
-//      shared-memory reads; FP32 with a conservative threshold, because the
-//      list only has to be a superset) and appends the hits to its neighbour
-//      list in HBM, laid out [entry][particle] so that both this write and
-//      the later read coalesce.
-// k_slots (latency bound; no shared memory, no block barriers)
-//   4. per distinct source body (ascending dem_id) the thread accumulates
-//      the slot sums in registers, four list entries in flight at a time --
-//      single pass: the distance sum of pass 2 is n . sum(XIJ m/rho W), so
-//      the reference's two pair loops collapse into one -- then applies the
-//      spring/dashpot/Coulomb law with the history carried in the sparse
-//      slot table,
-//   5. writes fx, fy, fz; k_bodies (rbx_bodies.cu) sums them per body with a
+//   3. groups the tile by source body (stable counting sort in shared
+//      memory), tests every particle against it (FP32 with a conservative
+//      threshold: the list only has to be a superset) and appends the hits
+//      to the particle's neighbour list in HBM, laid out [entry][particle].
+// k_list_sort (HBM bound; only on list rebuilds): work items ordered by list
+//   length per window of 256 particles, lists transposed into that order.
+// k_slots (FP64 issue / latency bound; every step): work item <-> particle
+//   4. walks its list, two entries per iteration, with the exact neighbour
+//      predicate; the sums of one source body live in registers -- single
+//      pass: the distance sum of the reference's second pair loop is
+//      n . sum(XIJ m/rho W), so the two loops collapse into one -- and at a
+//      body's last entry a contact prefilter either drops the slot or parks
+//      it in shared memory,
+//   5. finalize_slots: normals, distance, spring/dashpot/Coulomb law with the
+//      history carried in the sparse slot table, for the parked slots in
+//      ascending dem_id,
+//   6. writes fx, fy, fz; k_bodies (rbx_bodies.cu) sums them per body with a
 //      fixed shuffle tree (deterministic).
 #include "rbx_common.cuh"
 #include <string.h>
@@ -53,9 +58,6 @@ struct SlotAcc {
 #endif
 #ifndef RBX_SLOTS_CTA
 #define RBX_SLOTS_CTA 32
-#endif
-#ifndef RBX_SLOTS_WIDE
-#define RBX_SLOTS_WIDE 2
 #endif
 #ifndef RBX_SLOTS_MINB
 #define RBX_SLOTS_MINB (512 / RBX_SLOTS_CTA)
@@ -798,7 +800,6 @@ k_slots(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
       }
     };
 
-#if RBX_SLOTS_WIDE == 2
     // Two list entries per iteration.  Their pair math is independent
     // straight-line code (no branch: a pair out of range has W = 0 and adds
     // nothing -- the quintic spline's support is the neighbour radius -- so
@@ -903,90 +904,6 @@ k_slots(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
       qc0 = qn0; c0x = g0x; c0y = g0y; c0z = g0z; c0h = g0h;
       qc1 = qn1; c1x = g1x; c1y = g1y; c1z = g1z; c1h = g1h;
     }
-#else
-    // software pipeline over the list: the list entry of e + 2 + kLd is being
-    // loaded (coalesced stream from HBM) and the positions of sources e + 1
-    // and e + 2 are being gathered (L1/L2) while the pair math of entry e
-    // runs -- one iteration is about a hundred instructions, less than an L2
-    // round trip under load even with four warps per scheduler.
-    int ql[kLd];
-    const int *cl = S.nbr_srt + t;
-#pragma unroll
-    for (int j = 0; j < kLd; j++) {
-      ql[j] = (2 + j < nlist) ? cl[(size_t)(2 + j) * n_rigid] : 0;
-    }
-    int qc = nlist > 0 ? cl[0] : 0;
-    int qa = nlist > 1 ? cl[n_rigid] : 0;
-    cl += (size_t)(2 + kLd) * n_rigid;
-    double sx, sy, sz, sh = 0., ax1, ay1, az1, ah1 = 0.;
-    {
-      const int qi = qc & 0x7fffffff, qj = qa & 0x7fffffff;
-      sx = S.x[qi]; sy = S.y[qi]; sz = S.z[qi];
-      if (!UNIFORM_H) sh = S.h[qi];
-      ax1 = S.x[qj]; ay1 = S.y[qj]; az1 = S.z[qj];
-      if (!UNIFORM_H) ah1 = S.h[qj];
-    }
-
-    // ---- pairs: every entry's pair math runs once and lands in the registers
-    //      of the open slot; a marked entry parks the slot ---------------------
-    {
-#pragma unroll 3
-      for (int e0 = 0; e0 < nlist; e0++) {
-        // stage G for entry e0 + 2, stage L for entry e0 + 2 + kLd
-        const int qn = ql[0];
-        const int qni = qn & 0x7fffffff;
-        const double gx = S.x[qni], gy = S.y[qni], gz = S.z[qni];
-        double gh = 0.;
-        if (!UNIFORM_H) gh = S.h[qni];
-#pragma unroll
-        for (int j = 0; j + 1 < kLd; j++) ql[j] = ql[j + 1];
-        ql[kLd - 1] = (e0 + 2 + kLd < nlist) ? *cl : 0;
-        cl += n_rigid;
-        const int qi = qc & 0x7fffffff;
-        const double x0 = px - sx, x1 = py - sy, x2 = pz - sz;
-        const double r2 = rbx_r2(x0, x1, x2);
-        // exact neighbour predicate on the list entry:
-        // the list was built with a skin, possibly several steps ago
-        if (r2 < hi2 || r2 < (UNIFORM_H ? hj2_u : rbx_h2(rs2, sh))) {
-          npairs++;
-          touched = true;
-          // 1/r from rsqrt (1 ulp) instead of sqrt + division: the sums
-          // below move by a few ulp (tolerance 1e-10), the dependent FP64
-          // chain per entry is 3x shorter.
-          const double rinv = rsqrt(r2);
-          const double rij = r2 * rinv;
-          const double hij = UNIFORM_H ? hij_u : 0.5 * (ph + sh);
-          const double wij = rbx_quintic<DIM>(rij, hij);
-          const double tmp2 = vol * wij;                 // :803  m/rho * W
-          const double tmp1 = tmp2 * rinv;               // :683  m/(rho r) * W
-          ax += x0 * tmp1; ay += x1 * tmp1; az += x2 * tmp1;   // :686-688
-          w1 += tmp2;                                    // :690  tmp1 * r
-          bx += x0 * tmp2; by += x1 * tmp2; bz += x2 * tmp2;   // :807 (n . sum)
-          // :809: the second weight sum equals the first (tmp1*r == tmp2)
-          // :811 closest source (+ tie rule Q6).  The reference compares
-          // correctly rounded distances; a squared distance smaller by more
-          // than a few ulp decides the same way without the square roots,
-          // and only a near tie takes the exact path.
-          bool take = r2 < r2thr * (1. - 1e-14);
-          if (!take && r2 <= r2thr * (1. + 1e-14)) {
-            const double rex = sqrt(r2);
-            const double rmin = (qmin >= 0) ? sqrt(r2thr) : rmin0;
-            take = rex < rmin;
-            if (!take && qmin >= 0 && rex == rmin)     // exact tie: lowest
-              take = qi < qmin;                        // global index wins
-          }
-          if (take) { r2thr = r2; qmin = qi; }
-        }
-        if (qc < 0) {                  // last entry of this source body
-          park(make_int2(qmin, touched ? qi : -1));
-          ax = ay = az = w1 = bx = by = bz = 0.;
-          r2thr = rmin0 * rmin0; qmin = -1; touched = false;
-        }
-        qc = qa; sx = ax1; sy = ay1; sz = az1; sh = ah1;
-        qa = qn; ax1 = gx; ay1 = gy; az1 = gz; ah1 = gh;
-      }
-    }
-#endif
     if (nk > 0) finalize_slots(&S, &P, &D, acc, ovf, nk, p, tid, (cnt_raw & kSplitBit) != 0, &so);
     nactive = so.nactive;
     if (so.nout < S.ks) S.hist_key_out[(size_t)so.nout * n_rigid + p] = -1;

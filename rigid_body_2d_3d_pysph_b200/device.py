@@ -118,6 +118,9 @@ class DeviceScene(object):
                 [pa.properties[n] for pa in self.arrays]), f64)
         self.P['dem_id'] = self._t(np.concatenate(
             [pa.properties['dem_id'] for pa in self.arrays]), i32)
+        if self.n_total and int(self.P['dem_id'].min().item()) < 0:
+            raise ValueError('dem_id must be >= 0 (-1 is the empty key of the '
+                             'sparse contact history)')
         body = []
         for pa in self.rigid:
             bid = pa.properties['body_id'].astype(np.int64)
