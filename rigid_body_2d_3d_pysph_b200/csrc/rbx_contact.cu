@@ -85,6 +85,7 @@ k_neighbours(RbxScene S, RbxCells C, RbxParams P, double reach) {
   __shared__ float4 t_f[RBX_TILE];
   __shared__ int t_dem[RBX_TILE];
   __shared__ int h_key[kHash];
+  __shared__ unsigned t_first[RBX_TILE / 32];   // per 32 tile entries: bit j = entry starts a source body
   __shared__ int g_off[kWarps][kHash];
   __shared__ int g_scan[kWarps];
   __shared__ double red[kWarps][6];
@@ -160,7 +161,6 @@ k_neighbours(RbxScene S, RbxCells C, RbxParams P, double reach) {
   unsigned long long ncand = 0;
   const int cap = S.list_cap;
   int *wp = S.nbr_pos + (valid ? p : 0);   // next list entry of this particle
-  int last_dem = kEmptyKey;                // dem_id of the previous entry
 
   // The list only has to be a SUPERSET of the neighbour set (k_slots applies
   // the exact FP64 predicate to every entry), so the candidate test runs in
@@ -256,6 +256,14 @@ k_neighbours(RbxScene S, RbxCells C, RbxParams P, double reach) {
       }
     }
     __syncthreads();  // grouped tile complete
+#pragma unroll
+    for (int k = 0; k < kGIter; k++) {
+      const int j = k * RBX_CHUNK + tid;
+      const bool first = j < tile_cnt && (j == 0 || t_dem[j] != t_dem[j - 1]);
+      const unsigned word = __ballot_sync(0xffffffffu, first);
+      if (lane == 0) t_first[k * kWarps + wid] = word;
+    }
+    __syncthreads();
     // (b) list predicate.  32 tile entries at a time: a branch-free pass
     // collects the hits in a bit mask, a second loop appends them -- the
     // append then runs once per hit of the busiest lane instead of once per
@@ -263,6 +271,10 @@ k_neighbours(RbxScene S, RbxCells C, RbxParams P, double reach) {
     // index of the source, bit 31 set when it starts a new source body.
     if (valid) {
       ncand += (unsigned long long)tile_cnt;
+      // `pending`: the next hit starts a new source body (always true for the
+      // first hit of a tile: a body continued from the previous tile is a
+      // split body, which k_slots adds up)
+      bool pending = true;
       for (int j0 = 0; j0 < tile_cnt; j0 += 32) {
         unsigned mask = 0u;
 #pragma unroll
@@ -273,20 +285,26 @@ k_neighbours(RbxScene S, RbxCells C, RbxParams P, double reach) {
         }
         const int left = tile_cnt - j0;
         if (left < 32) mask &= (1u << left) - 1u;
+        const unsigned bounds = t_first[j0 >> 5];   // body boundaries of this block
+        unsigned seen = 0u;                          // positions up to the previous hit
+        const float *tw = &t_f[j0].w;
         while (mask) {
-          const int j = j0 + __ffs((int)mask) - 1;
+          const int b = __ffs((int)mask) - 1;
           mask &= mask - 1u;
+          const unsigned upto = (2u << b) - 1u;      // positions 0..b (b = 31: all)
+          const bool first = pending || (bounds & upto & ~seen) != 0u;
+          seen = upto;
+          pending = false;
           if (nlist < cap) {
-            const int d = t_dem[j];
-            const unsigned q = (unsigned)__float_as_int(t_f[j].w);
-            *wp = (int)(d != last_dem ? (q | kRunBit) : q);
+            const unsigned q = (unsigned)__float_as_int(tw[4 * b]);
+            *wp = (int)(first ? (q | kRunBit) : q);
             wp += n_rigid;
-            last_dem = d;
             nlist++;
           } else {
             list_overflow = true;
           }
         }
+        pending = pending || (bounds & ~seen) != 0u;  // a body started after the last hit
       }
     }
     __syncthreads();  // tiles may be overwritten
