@@ -61,6 +61,24 @@ def select_halo(cols, intervals, rank):
     return out
 
 
+def select_sources_by_body(x, own_src, src_start, src_count, xcm_x, rmax,
+                           lo, hi):
+    """Positions k in `own_src` with lo <= x[own_src[k]] <= hi, ascending --
+    the rows select_halo would pick -- found by testing only the sources of
+    the bodies whose bounding sphere [xcm - rmax, xcm + rmax] reaches the
+    interval.  own_src is ascending and grouped by body: the sources of body
+    b are own_src[src_start[b] : src_start[b] + src_count[b]]."""
+    dev = own_src.device
+    bsel = torch.nonzero((xcm_x + rmax >= lo) & (xcm_x - rmax <= hi)).flatten()
+    cnt = src_count[bsel]
+    first = src_start[bsel]
+    rep = torch.repeat_interleave(torch.arange(bsel.numel(), device=dev), cnt)
+    off = torch.cumsum(cnt, 0) - cnt
+    pos = first[rep] + (torch.arange(rep.numel(), device=dev) - off[rep])
+    xs = x[own_src[pos]]
+    return pos[torch.nonzero((xs >= lo) & (xs <= hi)).flatten()]
+
+
 def exchange_rows(cols, rows, rank, world, group=None):
     """Send cols[rows[q]] to rank q, receive what the others send here.
     Returns the received rows concatenated in rank order ([m, HALO_COLS])."""
@@ -172,18 +190,9 @@ class SlabScene(object):
             # bodies that can reach into q's interval, then only their
             # sources are tested (a few per cent of the slab): the same set,
             # in the same ascending order, as testing every own source
-            bsel = torch.nonzero((xc + rb >= lo_q) &
-                                 (xc - rb <= hi_q)).flatten()
-            cnt = self.src_count[bsel]
-            first = self.src_start[bsel]
-            rep = torch.repeat_interleave(
-                torch.arange(bsel.numel(), device=dev), cnt)
-            off = torch.cumsum(cnt, 0) - cnt
-            pos = first[rep] + (torch.arange(rep.numel(), device=dev) -
-                                off[rep])
-            xs = P['x'][idx[pos]]
-            rows.append(pos[torch.nonzero((xs >= lo_q) &
-                                          (xs <= hi_q)).flatten()])
+            rows.append(select_sources_by_body(
+                P['x'], idx, self.src_start, self.src_count, xc, rb,
+                lo_q, hi_q))
         gsel = idx[torch.cat(rows)]
         cols = self._pack(gsel)
         # rows of `cols` per destination are consecutive blocks

@@ -92,3 +92,34 @@ def test_slab_scenes_tile_the_full_scene():
     for a in (a0, a1):
         b, w = a[0], a[1]
         assert w.x.min() <= b.x.min() - 0.15 and w.x.max() >= b.x.max() + 0.15
+
+
+def test_body_level_selection_equals_full_scan():
+    """The rebuild-step halo selection narrows to the bodies whose bounding
+    sphere reaches the neighbour's interval before it tests particles; it has
+    to pick exactly the rows, in the order, of a scan over every own source
+    (parallel.select_halo)."""
+    from rigid_body_2d_3d_pysph_b200 import parallel
+    arrays, _, info = synthetic_pile(NB, slab=(0, 2))
+    body = arrays[0]
+    nb = int(body.nb[0])
+    x = torch.from_numpy(body.x)
+    own_src = torch.from_numpy(
+        np.nonzero(body.contact_force_is_boundary == 1.)[0])
+    bid = torch.from_numpy(body.body_id.astype(np.int64))
+    cnt = torch.bincount(bid[own_src], minlength=nb)
+    start = torch.cumsum(cnt, 0) - cnt
+    xcm = torch.from_numpy(np.asarray(body.xcm).reshape(-1, 3)[:, 0].copy())
+    r0 = np.sqrt(body.dx0**2 + body.dy0**2 + body.dz0**2)
+    rmax = torch.from_numpy(np.array([r0[body.body_id == b].max()
+                                      for b in range(nb)]))
+    xs = x[own_src]
+    lo0, hi0 = float(x.min()), float(x.max())
+    span = hi0 - lo0
+    for lo, hi in [(hi0 - 0.2 * span, hi0 + 1.0), (lo0 - 1.0, lo0 + 0.05),
+                   (lo0 + 0.4 * span, lo0 + 0.45 * span),
+                   (hi0 + 0.5, hi0 + 1.0), (lo0 - 1.0, hi0 + 1.0)]:
+        want = torch.nonzero((xs >= lo) & (xs <= hi)).flatten()
+        got = parallel.select_sources_by_body(x, own_src, start, cnt, xcm,
+                                              rmax, lo, hi)
+        assert torch.equal(got, want), (lo, hi, got.numel(), want.numel())
