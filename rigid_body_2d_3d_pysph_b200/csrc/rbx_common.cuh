@@ -97,6 +97,10 @@ __device__ __forceinline__ double rbx_rsqrt(double x) {
   return fma(fma(e, 0.375, 0.5), y * e, y);
 }
 
+__device__ __forceinline__ void rbx_prefetch_l2(const void *p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 __device__ __forceinline__ int rbx_cell_coord(double x, double x0, double inv, int n) {
   int c = (int)floor((x - x0) * inv);
   return c < 0 ? 0 : (c >= n ? n - 1 : c);

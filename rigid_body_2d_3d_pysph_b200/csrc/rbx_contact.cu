@@ -771,14 +771,36 @@ k_slots(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
   // work item t <-> particle nbr_order[t] (k_list_sort): full warps of equal
   // list length.  The per-body force/torque sum is done by k_bodies.
   const int tid = threadIdx.x, lane = tid & 31;
-  const int t = blockIdx.x * kSlotsCta + tid;
-  const bool valid = t < S.n_rigid;
   const size_t n_rigid = (size_t)S.n_rigid;
-
   unsigned nactive = 0, npairs = 0;
+
+  // Persistent CTAs, every one resident from the start, striding over the
+  // blocks of kSlotsCta work items (the grid size is odd: a stride that is a
+  // multiple of the 8 warps of a sort window would give a CTA the same length
+  // class every time).  A finished warp takes its next block at once instead
+  // of waiting for a CTA launch.
+  const int nitems = (S.n_rigid + kSlotsCta - 1) / kSlotsCta;
+  // particle and list length of the work item after this one: loaded a whole
+  // item ahead, so that its particle data and first list rows can be pulled
+  // into L2 while this item finishes (a warp otherwise starts every item with
+  // three dependent DRAM round trips and nothing to overlap them with)
+  int p_next = -1, cnt_next = 0;
+  {
+    const int t0 = blockIdx.x * kSlotsCta + tid;
+    if (t0 < S.n_rigid) { p_next = S.nbr_order[t0]; cnt_next = S.nbr_cnt_srt[t0]; }
+  }
+  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+  const int t = item * kSlotsCta + tid;
+  const bool valid = t < S.n_rigid;
+  const int p = p_next;
+  const int cnt_raw = cnt_next;
+  const int tn = t + gridDim.x * kSlotsCta;
+  p_next = -1;
+  if (item + gridDim.x < nitems && tn < S.n_rigid) {
+    p_next = S.nbr_order[tn];
+    cnt_next = S.nbr_cnt_srt[tn];
+  }
   if (valid) {
-    const int p = S.nbr_order[t];
-    const int cnt_raw = S.nbr_cnt_srt[t];
     const int nlist = cnt_raw & (kSplitBit - 1);
     // partial slots of a split body and the slots of a diagnostics run are
     // all parked; otherwise only those that pass the contact prefilter
@@ -922,8 +944,18 @@ k_slots(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
       qc0 = qn0; c0x = g0x; c0y = g0y; c0z = g0z; c0h = g0h;
       qc1 = qn1; c1x = g1x; c1y = g1y; c1z = g1z; c1h = g1h;
     }
+    if (p_next >= 0) {
+      rbx_prefetch_l2(S.x + p_next); rbx_prefetch_l2(S.y + p_next); rbx_prefetch_l2(S.z + p_next);
+      rbx_prefetch_l2(S.h + p_next); rbx_prefetch_l2(S.m + p_next); rbx_prefetch_l2(S.rho + p_next);
+      rbx_prefetch_l2(S.body + p_next);
+      const int *ln = S.nbr_srt + tn;
+      const int nl = cnt_next & (kSplitBit - 1);
+#pragma unroll
+      for (int k = 0; k < 2 + kLd; k++)
+        if (k < nl) rbx_prefetch_l2(ln + (size_t)k * n_rigid);
+    }
     if (nk > 0) finalize_slots(&S, &P, &D, acc, ovf, nk, p, tid, (cnt_raw & kSplitBit) != 0, &so);
-    nactive = so.nactive;
+    nactive += so.nactive;
     if (so.nout < S.ks) S.hist_key_out[(size_t)so.nout * n_rigid + p] = -1;
     if (D.key)
       for (int k2 = so.ki; k2 < RBX_MAX_KEYS; k2++) D.key[(size_t)k2 * n_rigid + p] = -1;
@@ -931,6 +963,7 @@ k_slots(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
     const double md = S.m[p];                        // BodyForce :122-125
     S.fx[p] = md * P.gx + so.cfx; S.fy[p] = md * P.gy + so.cfy; S.fz[p] = md * P.gz + so.cfz;
   }
+  }  // work-item loop
 
   if (S.counters) {
     unsigned na = nactive, np_ = npairs;
@@ -984,7 +1017,10 @@ extern "C" int rbx_contact_slots(const RbxScene *scene, const RbxCells *cells,
   RbxDiag d;
   if (diag) d = *diag; else memset(&d, 0, sizeof(d));
   const bool uni = params->h_uniform > 0.;
-  const int ng = rbx_blocks(scene->n_rigid, kSlotsCta);
+  // all CTAs resident at once (RBX_SLOTS_MINB per SM on 148 SMs), odd count
+  int ng = rbx_blocks(scene->n_rigid, kSlotsCta);
+  const int resident = 148 * RBX_SLOTS_MINB - 1;
+  if (ng > resident) ng = resident;
   if (scene->dim == 3) {
     if (uni) k_slots<3, true><<<ng, kSlotsCta, 0, st>>>(*scene, *params, d, params->h_uniform);
     else k_slots<3, false><<<ng, kSlotsCta, 0, st>>>(*scene, *params, d, 0.);
