@@ -450,9 +450,9 @@ def main():
                    min(args.settle, args.cpu_settle), args.cpu_steps)}
 
     if rank == 0:
-        launches_per_step = 17   # bodies, pose, 8 cell-list kernels,
+        launches_per_step = 18   # bodies, pose, 8 cell-list kernels,
         #                          k_neighbours, k_list_sort, list commit + clear,
-        #                          k_slots, bodies, pose (memsets not
+        #                          k_slots, bodies (reduce), bodies (kick), pose (memsets not
         #                          counted; the cell-list kernels and
         #                          k_neighbours return at once on steps
         #                          that reuse the neighbour lists)

@@ -348,7 +348,12 @@ extern "C" int rbx_gtvf_step(const RbxScene *scene, const RbxPoints *src, const 
   if ((rc = rbx_cells_build(src, cells, params->reach, scene->status, workspace,
                             workspace_bytes, stream))) return rc;
   if ((rc = rbx_contact_mofidi(scene, cells, params, nullptr, stream))) return rc;
-  if ((rc = launch_bodies(scene, 1 | 2, params->dt, 0., st))) return rc;
+  // reduce (warp per body, streams 48 B per particle) and kick (thread per
+  // body) as two launches: with the kick's divisions on lane 0 of every
+  // reduce warp, the warp sits on its slot three times longer than its loads
+  // take and the reduction runs at a third of the HBM bandwidth
+  if ((rc = launch_bodies(scene, 1, params->dt, 0., st))) return rc;
+  if ((rc = launch_bodies(scene, 2, params->dt, 0., st))) return rc;
   if (!(flags & 1))
     if ((rc = rbx_pose_particles(scene, RBX_POSE_VEL, stream))) return rc;
   return RBX_OK;
