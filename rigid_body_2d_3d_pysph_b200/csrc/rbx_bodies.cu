@@ -121,49 +121,43 @@ __device__ __forceinline__ void drift_body(const RbxScene &S, int b, double dt) 
   rotate_body(S.R + i9, S.R + i9, om, dt, S.iinv_b + i9, S.planar ? nullptr : S.iinv_g + i9);
 }
 
-// mode bits: 1 = reduce, 2 = kick, 4 = drift, 8 = kick before drift
-// order executed: [reduce] [kick (post)] [kick (pre)] [drift]
-// The reduction wants a warp per body (lanes stride over its particles); the
-// 3x3 algebra of kick and drift (a few hundred dependent FP64 instructions
-// with divisions and square roots) is one thread's work -- with the reduce
-// bit clear the launch is a thread per body, 32 bodies per warp instead of
-// one warp idling 31 lanes per body.
-__global__ void k_bodies(RbxScene S, int mode, double dt, double skin) {
-  const int gt = blockIdx.x * blockDim.x + threadIdx.x;
-  if (!(mode & 1)) {
-    if (gt >= S.n_bodies) return;
-    if (mode & 2) kick_body(S, gt, dt / 2.);
-    if (mode & 8) kick_body(S, gt, dt / 2.);
-    if (mode & 4) { drift_body(S, gt, dt); check_displacement(S, gt, skin); }
-    return;
-  }
-  const int warp = gt >> 5;
+// SumUpExternalForces.reduce :158-175, a warp per body: lanes stride over the
+// body's particles (contiguous), fixed shuffle tree => deterministic.  A
+// kernel of its own (few registers, short-lived warps): it streams 48 bytes
+// per particle and should run at HBM speed.
+__global__ void __launch_bounds__(128, 8) k_reduce(RbxScene S) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= S.n_bodies) return;
   const int b = warp;
-  {
-    // SumUpExternalForces.reduce :158-175: lanes stride over the body's
-    // particles (contiguous), fixed shuffle tree => deterministic
-    double v6[6] = {0, 0, 0, 0, 0, 0};
-    const int q0 = S.chunk_start[S.body_chunk[b]], q1 = S.chunk_start[S.body_chunk[b + 1]];
-    const double cx = S.xcm[3 * b], cy = S.xcm[3 * b + 1], cz = S.xcm[3 * b + 2];
+  double v6[6] = {0, 0, 0, 0, 0, 0};
+  const int q0 = S.chunk_start[S.body_chunk[b]], q1 = S.chunk_start[S.body_chunk[b + 1]];
+  const double cx = S.xcm[3 * b], cy = S.xcm[3 * b + 1], cz = S.xcm[3 * b + 2];
 #pragma unroll 4
-    for (int q = q0 + lane; q < q1; q += 32) {
-      const double fx = S.fx[q], fy = S.fy[q], fz = S.fz[q];
-      const double dx = S.x[q] - cx, dy = S.y[q] - cy, dz = S.z[q] - cz;
-      v6[0] += fx; v6[1] += fy; v6[2] += fz;
-      v6[3] += (dy * fz - dz * fy);
-      v6[4] += (dz * fx - dx * fz);
-      v6[5] += (dx * fy - dy * fx);
-    }
-#pragma unroll
-    for (int a = 0; a < 6; a++) v6[a] = rbx_warp_sum(v6[a]);
-    if (lane == 0) {
-#pragma unroll
-      for (int a = 0; a < 3; a++) { S.force[3 * b + a] = v6[a]; S.torque[3 * b + a] = v6[3 + a]; }
-    }
+  for (int q = q0 + lane; q < q1; q += 32) {
+    const double fx = S.fx[q], fy = S.fy[q], fz = S.fz[q];
+    const double dx = S.x[q] - cx, dy = S.y[q] - cy, dz = S.z[q] - cz;
+    v6[0] += fx; v6[1] += fy; v6[2] += fz;
+    v6[3] += (dy * fz - dz * fy);
+    v6[4] += (dz * fx - dx * fz);
+    v6[5] += (dx * fy - dy * fx);
   }
-  if (lane != 0) return;
+#pragma unroll
+  for (int a = 0; a < 6; a++) v6[a] = rbx_warp_sum(v6[a]);
+  if (lane == 0) {
+#pragma unroll
+    for (int a = 0; a < 3; a++) { S.force[3 * b + a] = v6[a]; S.torque[3 * b + a] = v6[3 + a]; }
+  }
+}
+
+// mode bits: 2 = kick, 4 = drift, 8 = kick before drift (1 = reduce: k_reduce)
+// order executed: [kick (post)] [kick (pre)] [drift]
+// The 3x3 algebra of kick and drift (a few hundred dependent FP64
+// instructions with divisions and square roots) is one thread's work: a
+// thread per body, 32 bodies per warp.
+__global__ void k_bodies(RbxScene S, int mode, double dt, double skin) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= S.n_bodies) return;
   if (mode & 2) kick_body(S, b, dt / 2.);
   if (mode & 8) kick_body(S, b, dt / 2.);
   if (mode & 4) { drift_body(S, b, dt); check_displacement(S, b, skin); }
@@ -272,8 +266,8 @@ __global__ void k_halo_unpack(RbxScene S, int first, int n, const double *rows) 
 int launch_bodies(const RbxScene *S, int mode, double dt, double skin, cudaStream_t st) {
   if (S->n_bodies <= 0) return RBX_OK;
   const int T = 128;
-  const long long threads = (mode & 1) ? (long long)S->n_bodies * 32 : S->n_bodies;
-  k_bodies<<<rbx_blocks(threads, T), T, 0, st>>>(*S, mode, dt, skin);
+  if (mode & 1) k_reduce<<<rbx_blocks((long long)S->n_bodies * 32, T), T, 0, st>>>(*S);
+  if (mode & ~1) k_bodies<<<rbx_blocks(S->n_bodies, T), T, 0, st>>>(*S, mode & ~1, dt, skin);
   RBX_CHECK_LAUNCH();
   return RBX_OK;
 }
@@ -348,12 +342,10 @@ extern "C" int rbx_gtvf_step(const RbxScene *scene, const RbxPoints *src, const 
   if ((rc = rbx_cells_build(src, cells, params->reach, scene->status, workspace,
                             workspace_bytes, stream))) return rc;
   if ((rc = rbx_contact_mofidi(scene, cells, params, nullptr, stream))) return rc;
-  // reduce (warp per body, streams 48 B per particle) and kick (thread per
-  // body) as two launches: with the kick's divisions on lane 0 of every
-  // reduce warp, the warp sits on its slot three times longer than its loads
-  // take and the reduction runs at a third of the HBM bandwidth
-  if ((rc = launch_bodies(scene, 1, params->dt, 0., st))) return rc;
-  if ((rc = launch_bodies(scene, 2, params->dt, 0., st))) return rc;
+  // reduce (k_reduce, warp per body) and kick (k_bodies, thread per body)
+  // are two launches: with the kick's divisions on lane 0 of every reduce
+  // warp, the warp sat on its slot three times longer than its loads take
+  if ((rc = launch_bodies(scene, 1 | 2, params->dt, 0., st))) return rc;
   if (!(flags & 1))
     if ((rc = rbx_pose_particles(scene, RBX_POSE_VEL, stream))) return rc;
   return RBX_OK;
