@@ -42,8 +42,9 @@ typedef enum {
 } RbxError;
 
 /* bits of the device status word */
-#define RBX_STATUS_SLOT_OVERFLOW 1u  /* > 32 bodies touch one particle (or the
-                                        diagnostics hold > RBX_MAX_KEYS)   */
+#define RBX_STATUS_SLOT_OVERFLOW 1u  /* > 32 source-body runs in one particle's
+                                        list (or the diagnostics hold >
+                                        RBX_MAX_KEYS)                         */
 #define RBX_STATUS_HIST_OVERFLOW 2u  /* > ks simultaneous contacts            */
 #define RBX_STATUS_LIST_OVERFLOW 4u  /* per-particle neighbour list full       */
 #define RBX_STATUS_GRID_COARSENED 8u /* cell size enlarged to fit cap_cells    */

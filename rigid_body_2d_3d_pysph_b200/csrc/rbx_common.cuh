@@ -7,7 +7,6 @@
 
 #define RBX_CHUNK 128     // threads per CTA = max particles per work item
 #define RBX_TILE 768      // staged source particles per shared-memory tile
-#define RBX_LISTMAX 127   // largest neighbour-list length the chunk sort keys on
 
 #define RBX_CHECK_LAUNCH()                                   \
   do {                                                       \

@@ -39,14 +39,7 @@
 
 namespace {
 
-struct SlotAcc {
-  double ax, ay, az, w1;  // sum XIJ*tmp1, sum tmp1*RIJ      (:686-690)
-  double bx, by, bz, w2;  // sum XIJ*tmp2, sum tmp2          (:807-809)
-  double rmin;            // closest_point_dist_to_source    (:811-818)
-  int pmin;               // sorted position of the closest source (-1 none)
-  int gmin;               // its global index (tie rule: lowest index)
-};
-
+// tuning knobs (variants: csrc/build.py build(defines=[...], out=...))
 #ifndef RBX_KLD
 #define RBX_KLD 4
 #endif
