@@ -212,3 +212,65 @@ def test_device_boundary_identification_equals_host():
                 (name, pa.name)
             assert host.is_boundary.sum() > 0
             assert np.abs(host.normal - dev.normal).max() < 1e-10
+
+
+def test_neighbour_list_structures():
+    """The data structures between the three contact kernels, on configs 3
+    and 4: nbr_pos lists grouped by source body with the first entry of a
+    body marked; nbr_order a permutation of every 256-particle window in
+    descending list length; nbr_srt the same lists, transposed into that
+    order, with the LAST entry of a body marked; and the lists a superset of
+    the exact neighbour sets restricted to gated sources."""
+    from rigid_body_2d_3d_pysph_b200.device import DeviceScene
+    from tests.util import load_config
+    for name in ('benchmark_5_3d', 'stack_of_cylinders'):
+        arrays, meta = load_config(name)
+        sc = DeviceScene(arrays, meta['rigid'], meta['boundaries'],
+                         dim=meta['dim'], kr=meta['kr'], kf=meta['kf'],
+                         fric_coeff=meta['fric_coeff'], gx=meta['gx'],
+                         gy=meta['gy'], gz=meta['gz'],
+                         planar=(meta['stepper'] == 'gtvf2d'))
+        sc.gtvf_step(meta['dt'], 1)
+        sc.check_status()
+        n, cap = sc.n_rigid, sc.list_cap
+        raw = sc.T['nbr_pos'].view(cap, n).cpu().numpy()
+        cnt = sc.T['nbr_cnt'].cpu().numpy()
+        srt = sc.T['nbr_srt'].view(cap, n).cpu().numpy()
+        order = sc.T['nbr_order'].cpu().numpy()
+        cnt_s = sc.T['nbr_cnt_srt'].cpu().numpy()
+        dem = sc.P['dem_id'].cpu().numpy()
+        x, y, z, h = (sc.P[k].cpu().numpy() for k in 'xyzh')
+        src = np.zeros(sc.n_total, bool)
+        src[sc.T['src_index'].cpu().numpy()] = True
+        lens = cnt & 0x3fffffff
+        assert lens.max() > 0, name
+        # windows of 256: a permutation, longest lists first
+        for w0 in range(0, n, 256):
+            o = order[w0:w0 + 256]
+            assert np.array_equal(np.sort(o), np.arange(w0, min(w0 + 256, n)))
+            assert np.all(np.diff(lens[o]) <= 0), (name, w0)
+        assert np.array_equal(cnt_s, cnt[order])
+        reach2 = (sc.reach + sc.skin)**2
+        for t in range(n):
+            p, ln = order[t], lens[order[t]]
+            a = raw[:ln, p].astype(np.int64)
+            b = srt[:ln, t].astype(np.int64)
+            qa, qb = a & 0x7fffffff, b & 0x7fffffff
+            assert np.array_equal(qa, qb), (name, p)
+            assert len(set(qa.tolist())) == ln            # no duplicates
+            assert src[qa].all() and (dem[qa] != dem[p]).all()
+            d = dem[qa]
+            first = np.r_[True, d[1:] != d[:-1]] if ln else np.zeros(0, bool)
+            last = np.r_[d[1:] != d[:-1], True] if ln else np.zeros(0, bool)
+            assert np.array_equal(a < 0, first), (name, p)  # bit 31 (int32 sign)
+            assert np.array_equal(b < 0, last), (name, p)
+            if not (cnt[p] >> 30) & 1:                     # one run per body
+                assert len(set(d[first].tolist())) == int(first.sum())
+            # superset of the gated sources within the reach (lists were
+            # built from the positions of this very step)
+            r2 = (x - x[p])**2 + (y - y[p])**2 + (z - z[p])**2
+            want = np.nonzero(src & (dem != dem[p]) &
+                              (r2 < 0.999 * (sc.radius_scale *
+                                             max(h[p], h.max()))**2))[0]
+            assert np.isin(want, qa).all(), (name, p)
+            assert (r2[qa] < 1.01 * reach2).all(), (name, p)
