@@ -41,7 +41,7 @@ namespace {
 
 // tuning knobs (variants: csrc/build.py build(defines=[...], out=...))
 #ifndef RBX_KLD
-#define RBX_KLD 4
+#define RBX_KLD 2
 #endif
 #ifndef RBX_KACC
 #define RBX_KACC 4
