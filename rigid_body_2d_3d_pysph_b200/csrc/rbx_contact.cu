@@ -454,11 +454,18 @@ __global__ void k_list_clear(RbxScene S, double skin) {
 //   * accumulates the sums of one source body in registers and parks the
 //     slot when the marked entry has been added: no key search, no
 //     shared-memory read-modify-write per pair.
-constexpr int kSortW = 256;       // particles per window = threads per CTA
+#ifndef RBX_SORT_W
+#define RBX_SORT_W 256
+#endif
+#ifndef RBX_SORT_ROWS
+#define RBX_SORT_ROWS 32
+#endif
+constexpr int kSortW = RBX_SORT_W;       // particles per window = threads per CTA
 constexpr int kSortBins = 256;
-constexpr int kSortRows = 32;     // list rows staged in shared memory at a time
+constexpr int kSortRows = RBX_SORT_ROWS; // list rows staged in shared memory at a time
+static_assert(kSortW >= kSortBins && kSortW % 32 == 0 && kSortW <= 1024, "kSortW");
 
-__global__ void __launch_bounds__(kSortW, 4)
+__global__ void __launch_bounds__(kSortW, 1024 / kSortW)
 k_list_sort(RbxScene S) {
   if (S.rebuild && *S.rebuild == 0u) return;      // lists still valid
   __shared__ int stage[kSortRows + 1][kSortW];    // [row][particle of the window]
