@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RBX_VERSION 202 /* 0.2.2 */
+#define RBX_VERSION 203 /* 0.2.3 */
 
 typedef enum {
   RBX_OK = 0,
@@ -208,10 +208,22 @@ typedef struct {
   uint32_t *status;
 } RbxDemScene;
 
+/* Inputs of the Canelas Hertz contact that RbxScene does not carry, all
+ * [n_total]: sphere radius, Young modulus and Poisson ratio of every particle
+ * (the reference reads the array constants d_E[0], s_E[0], ...), and the
+ * global body index of the particle (-1: not part of a rigid body -> the
+ * RigidWall law).                                                         */
+typedef struct {
+  const double *rad_s, *E, *nu;
+  const int32_t *src_body;
+  double Cn;         /* damping constant, 1.4e-5 in the reference */
+} RbxCanelas;
+
 int rbx_version(void);
 const char *rbx_strerror(int code);
 /* sizeof(RbxGridInfo, RbxPoints, RbxCells, RbxScene, RbxParams, RbxDiag) for
- * which = 0..5, RbxDemScene for 6: lets a binding check its struct mirrors. */
+ * which = 0..5, RbxDemScene for 6, RbxCanelas for 7: lets a binding check its
+ * struct mirrors.                                                         */
 size_t rbx_sizeof(int which);
 
 /* Scratch bytes needed by rbx_cells_build for a cell list of this capacity. */
@@ -249,6 +261,14 @@ int rbx_contact_neighbours(const RbxScene *scene, const RbxCells *cells,
 int rbx_contact_slots(const RbxScene *scene, const RbxCells *cells,
                       const RbxParams *params, const RbxDiag *diag,
                       void *stream);
+
+/* BodyForce.initialize + RigidBodyCanelasRigidRigid.loop +
+ * RigidBodyCanelasRigidWall.loop (rigid_body_common.py:115-125, 244-628;
+ * tangential part disabled upstream) over the cell list `cells` of the
+ * source particles: fx, fy, fz of every rigid particle.                     */
+int rbx_contact_canelas(const RbxScene *scene, const RbxCells *cells,
+                        const RbxParams *params, const RbxCanelas *canelas,
+                        void *stream);
 
 /* SumUpExternalForces.reduce (rigid_body_common.py:128-175): fx,fy,fz,x,y,z
  * -> force[3nb], torque[3nb], one warp per body, fixed order

@@ -325,6 +325,73 @@ def run_dem_case():
         'dem2d', nsteps, meta['seconds'], sand.total_tng_contacts.sum()))
 
 
+def run_canelas_case():
+    """RigidBodyCanelasRigidRigid / RigidBodyCanelasRigidWall
+    (rigid_body_common.py:244-628).  No scheme of the reference wires them;
+    the group below is the obvious one: BodyForce + the two Hertz loops, then
+    SumUpExternalForces.  The tangential-history properties their signatures
+    name (and never touch, the tangential part is commented out) are added."""
+    from pysph.sph.equation import Group
+    dx = 0.025
+    h = 1.3 * dx
+    xb, yb = get_2d_block(dx, 3 * dx, 3 * dx)
+    n = len(xb)
+    x = np.concatenate([xb, xb + 4 * dx - 0.04 * dx])
+    y = np.concatenate([yb, yb + 0.12 * dx])
+    bid = np.concatenate([np.zeros(n, int), np.ones(n, int)])
+    body = _body('body', x, y, np.zeros(2 * n), dx, h, 2000., 2, bid, bid, 3)
+    xw = (np.arange(16) - 5.5) * dx + 0.07 * dx
+    wall = _wall('wall', xw, np.full(16, yb.min() - 0.97 * dx), np.zeros(16),
+                 dx, h, 2000., 2, 2)
+    s = rigid_body_3d.RigidBody3DScheme(['body'], ['wall'], dim=2, gy=-9.81)
+    _finish(s, [body], [wall])
+    s.set_linear_velocity(body, np.array([0.3, -0.2, 0., -0.4, 0.1, 0.]))
+    s.set_angular_velocity(body, np.array([0., 0., 2., 0., 0., -3.]))
+    limit = 6
+    body.add_constant('max_tng_contacts_limit', [limit])
+    for nme in ('tng_idx', 'tng_idx_dem_id'):
+        body.add_property(nme, type='int', stride=limit)
+        body.properties[nme][:] = -1
+    for nme in ('tng_fx', 'tng_fy', 'tng_fz'):
+        body.add_property(nme, stride=limit)
+    body.add_property('total_tng_contacts', type='int')
+    arrays = [body, wall]
+    st = {'body': rigid_body_3d.GTVFRigidBody3DStep()}
+    kernel = QuinticSpline(dim=2)
+    dt = 1e-6
+    # stage 1 + 2 of one GTVF step give the particles their rigid-body
+    # velocities and positions; then one force evaluation
+    interp.run_stage(st['body'], 'stage1', body, 0., dt)
+    interp.run_stage(st['body'], 'stage2', body, 0., dt)
+    Cn = 1.4e-5
+    groups = [Group(equations=[
+        rigid_body_common.BodyForce(dest='body', sources=None, gx=0.,
+                                    gy=-9.81, gz=0.),
+        rigid_body_common.RigidBodyCanelasRigidRigid(
+            dest='body', sources=['body'], Cn=Cn),
+        rigid_body_common.RigidBodyCanelasRigidWall(
+            dest='body', sources=['wall'], Cn=Cn)]),
+        Group(equations=[rigid_body_common.SumUpExternalForces(
+            dest='body', sources=None)])]
+    meta = {'name': 'canelas2d', 'rigid': ['body'], 'boundaries': ['wall'],
+            'dim': 2, 'dt': dt, 'gx': 0., 'gy': -9.81, 'gz': 0., 'Cn': Cn,
+            'kr': s.kr, 'kf': s.kf, 'fric_coeff': s.fric_coeff,
+            'stepper': 'gtvf3d'}
+    dump(os.path.join(GOLDEN, 'canelas2d_scene.npz'), arrays, {'t': 0.0},
+         detailed_output=True, compress=True)
+    interp.run_groups(groups, arrays, kernel, 0., dt)
+    out = {}
+    for nme in ('fx', 'fy', 'fz'):
+        out['ref/1/body/' + nme] = body.properties[nme].copy()
+    for nme in ('force', 'torque'):
+        out['ref/1/body/' + nme] = np.asarray(body.constants[nme]).copy()
+    out['__meta__'] = np.array(json.dumps(meta))
+    np.savez_compressed(os.path.join(GOLDEN, 'canelas2d_ref.npz'), **out)
+    f = np.abs(body.fy).max()
+    print('%-16s |fy|max %.4g  (m g = %.4g)' % ('canelas2d', f,
+                                               body.m[0] * 9.81))
+
+
 def known_answers():
     """Reference-owned numeric pins."""
     dx = 0.1
@@ -362,11 +429,13 @@ CASES = {
 
 if __name__ == '__main__':
     os.makedirs(GOLDEN, exist_ok=True)
-    which = sys.argv[1:] or list(CASES) + ['known', 'dem2d']
+    which = sys.argv[1:] or list(CASES) + ['known', 'dem2d', 'canelas2d']
     for name in which:
         if name == 'known':
             known_answers()
         elif name == 'dem2d':
             run_dem_case()
+        elif name == 'canelas2d':
+            run_canelas_case()
         else:
             run_case(CASES[name]())

@@ -199,6 +199,22 @@ def rk2_step(arrays, rigid_names, params, fix_q7=False, ks=0, nsteps=1):
     return counts
 
 
+def canelas(arrays, rigid_names, params, Cn=1.4e-5):
+    """BodyForce + RigidBodyCanelasRigidRigid/RigidWall + SumUpExternalForces
+    (rigid_body_common.py:115-125, 244-628, 128-175); E and poisson_ratio are
+    the arrays' constants."""
+    L = lib()
+    arr, keep = pack(arrays, rigid_names)
+    E = np.array([float(pa.constants['E'][0]) for pa in arrays])
+    nu = np.array([float(pa.constants['poisson_ratio'][0]) for pa in arrays])
+    L.rbo_canelas.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                              ctypes.c_void_p, ctypes.c_void_p,
+                              ctypes.c_double]
+    L.rbo_canelas(arr, len(arrays), ctypes.byref(params),
+                  E.ctypes.data_as(ctypes.c_void_p),
+                  nu.ctypes.data_as(ctypes.c_void_p), float(Cn))
+
+
 def num_threads():
     return lib().rbo_num_threads()
 

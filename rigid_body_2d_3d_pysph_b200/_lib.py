@@ -81,6 +81,11 @@ class RbxParams(ctypes.Structure):
                 ('h_uniform', c_f64), ('skin', c_f64)]
 
 
+class RbxCanelas(ctypes.Structure):
+    _fields_ = [('rad_s', c_vp), ('E', c_vp), ('nu', c_vp),
+                ('src_body', c_vp), ('Cn', c_f64)]
+
+
 class RbxDiag(ctypes.Structure):
     _fields_ = [('key', c_vp), ('closest', c_vp), ('nx', c_vp), ('ny', c_vp),
                 ('nz', c_vp), ('dist', c_vp), ('overlap', c_vp),
@@ -91,7 +96,7 @@ class RbxDiag(ctypes.Structure):
 SYMBOLS = ['rbx_version', 'rbx_strerror', 'rbx_sizeof',
            'rbx_cells_workspace_bytes', 'rbx_cells_build', 'rbx_pairs_dump',
            'rbx_contact_mofidi', 'rbx_contact_neighbours',
-           'rbx_contact_slots', 'rbx_reduce_bodies', 'rbx_gtvf_kick',
+           'rbx_contact_slots', 'rbx_contact_canelas', 'rbx_reduce_bodies', 'rbx_gtvf_kick',
            'rbx_gtvf_drift', 'rbx_pose_particles', 'rbx_halo_pack',
            'rbx_halo_unpack', 'rbx_rk2_stage',
            'rbx_gtvf_step', 'rbx_contact_lvc', 'rbx_dem_step',
@@ -136,6 +141,8 @@ def load():
                                          P(RbxParams), c_vp]
     L.rbx_contact_slots.argtypes = [P(RbxScene), P(RbxCells), P(RbxParams),
                                     P(RbxDiag), c_vp]
+    L.rbx_contact_canelas.argtypes = [P(RbxScene), P(RbxCells), P(RbxParams),
+                                      P(RbxCanelas), c_vp]
     L.rbx_reduce_bodies.argtypes = [P(RbxScene), c_vp]
     L.rbx_gtvf_kick.argtypes = [P(RbxScene), c_f64, c_vp]
     L.rbx_gtvf_drift.argtypes = [P(RbxScene), c_f64, c_f64, c_vp]
@@ -154,7 +161,7 @@ def load():
                                         ctypes.c_int, c_f64, c_vp, c_vp, c_vp,
                                         c_vp, c_vp, c_vp]
     for i, cls in enumerate([RbxGridInfo, RbxPoints, RbxCells, RbxScene,
-                             RbxParams, RbxDiag, RbxDemScene]):
+                             RbxParams, RbxDiag, RbxDemScene, RbxCanelas]):
         if L.rbx_sizeof(i) != ctypes.sizeof(cls):
             raise RbxError('ABI mismatch for %s: library %d bytes, binding %d'
                            % (cls.__name__, L.rbx_sizeof(i),

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 SOURCES = ['rbx_cells.cu', 'rbx_contact.cu', 'rbx_bodies.cu', 'rbx_lvc.cu',
-           'rbx_setup.cu']
+           'rbx_setup.cu', 'rbx_canelas.cu']
 LIB = os.path.join(HERE, 'librbx.so')
 
 

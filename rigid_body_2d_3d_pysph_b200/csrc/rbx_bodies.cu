@@ -374,6 +374,7 @@ extern "C" size_t rbx_sizeof(int which) {
     case 4: return sizeof(RbxParams);
     case 5: return sizeof(RbxDiag);
     case 6: return sizeof(RbxDemScene);
+    case 7: return sizeof(RbxCanelas);
     default: return 0;
   }
 }

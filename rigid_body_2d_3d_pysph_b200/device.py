@@ -345,6 +345,7 @@ class DeviceScene(object):
         c.cond = _ptr(self.rebuild)     # skip the build while lists are valid
         self._cells = c
         self._graph = None
+        self._canelas = None
         self.rebuild.fill_(1)
 
     def points(self, index=None, n=None):
@@ -471,6 +472,68 @@ class DeviceScene(object):
             ctypes.byref(p), ctypes.byref(diag) if diag is not None else None,
             self.stream), 'rbx_contact_mofidi')
         self.parity ^= 1
+
+    def contact_canelas(self, dt, Cn=1.4e-5):
+        """BodyForce + RigidBodyCanelasRigidRigid / RigidBodyCanelasRigidWall
+        (rigid_body_common.py:115-125, 244-628): fx, fy, fz of every rigid
+        particle from the Hertz contact of the ``rad_s`` spheres of ALL
+        particles of the scene (the equations have no boundary gate).  Every
+        array needs the property ``rad_s`` and the constants ``E`` and
+        ``poisson_ratio``.  Follow with ``reduce_bodies()``."""
+        self.push_touched()
+        if getattr(self, '_canelas', None) is None:
+            f64, i32 = torch.float64, torch.int32
+            for pa in self.arrays:
+                for n in ('E', 'poisson_ratio'):
+                    if n not in pa.constants:
+                        raise KeyError("array '%s' has no constant %s" %
+                                       (pa.name, n))
+                if 'rad_s' not in pa.properties:
+                    raise KeyError("array '%s' has no property rad_s" %
+                                   pa.name)
+            cat = np.concatenate
+            t = {'rad_s': self._t(cat([pa.properties['rad_s']
+                                       for pa in self.arrays]), f64),
+                 'E': self._t(cat([np.full(pa.get_number_of_particles(),
+                                           float(pa.constants['E'][0]))
+                                   for pa in self.arrays]), f64),
+                 'nu': self._t(cat([np.full(
+                     pa.get_number_of_particles(),
+                     float(pa.constants['poisson_ratio'][0]))
+                     for pa in self.arrays]), f64)}
+            sb = torch.full((max(self.n_total, 1),), -1, dtype=i32,
+                            device=self.device)
+            sb[:self.n_rigid] = self.P['body']
+            t['src_body'] = sb
+            # a cell list of its own over all particles
+            saved = (self.C, self.cap_cells, self.cap_points, self.workspace)
+            self._alloc_cells(max(self.n_total, 1), torch.arange(
+                self.n_total, dtype=i32, device=self.device))
+            c = RbxCells()
+            c.cap_cells, c.cap_points = self.cap_cells, self.cap_points
+            for n in ['info', 'cell_start', 'cell_of', 'rank', 'gidx', 'sx',
+                      'sy', 'sz', 'sh', 'sdem']:
+                setattr(c, n, _ptr(self.C[n]))
+            c.cond = None
+            t['C'], t['workspace'], t['cells'] = self.C, self.workspace, c
+            (self.C, self.cap_cells, self.cap_points, self.workspace) = saved
+            k = _lib.RbxCanelas()
+            k.rad_s, k.E, k.nu = _ptr(t['rad_s']), _ptr(t['E']), _ptr(t['nu'])
+            k.src_body = _ptr(t['src_body'])
+            t['struct'] = k
+            self._canelas = t
+        t = self._canelas
+        t['struct'].Cn = float(Cn)
+        _lib.check(self.lib.rbx_cells_build(
+            ctypes.byref(self.points()), ctypes.byref(t['cells']), self.reach,
+            _ptr(self.status), _ptr(t['workspace']), t['workspace'].numel(),
+            self.stream), 'rbx_cells_build')
+        p = self.params(dt)
+        _lib.check(self.lib.rbx_contact_canelas(
+            ctypes.byref(self.scene), ctypes.byref(t['cells']),
+            ctypes.byref(p), ctypes.byref(t['struct']), self.stream),
+            'rbx_contact_canelas')
+        self.mark_device_newer()
 
     def reduce_bodies(self):
         _lib.check(self.lib.rbx_reduce_bodies(ctypes.byref(self.scene),

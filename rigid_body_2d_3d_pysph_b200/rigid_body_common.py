@@ -181,3 +181,21 @@ class ComputeContactForce(Equation):
         self.kf = kf
         self.fric_coeff = fric_coeff
         super(ComputeContactForce, self).__init__(dest, sources)
+
+
+class RigidBodyCanelasRigidRigid(Equation):
+    """rigid_body_common.py:244-442 -> rbx_contact_canelas
+    (``DeviceScene.contact_canelas``).  No scheme of the reference wires the
+    Canelas equations; the planner does not accept them in a group list."""
+
+    def __init__(self, dest, sources, Cn=1.4 * 1e-5):
+        self.Cn = Cn
+        super(RigidBodyCanelasRigidRigid, self).__init__(dest, sources)
+
+
+class RigidBodyCanelasRigidWall(Equation):
+    """rigid_body_common.py:445-628 -> rbx_contact_canelas."""
+
+    def __init__(self, dest, sources, Cn=1.4 * 1e-5):
+        self.Cn = Cn
+        super(RigidBodyCanelasRigidWall, self).__init__(dest, sources)
