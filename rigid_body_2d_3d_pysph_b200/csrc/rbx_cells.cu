@@ -24,8 +24,12 @@ constexpr int kScanTile = kScanThreads * kScanItems;
 #define RBX_SKIP_IF_VALID(C) do { if ((C).cond && *(C).cond == 0u) return; } while (0)
 
 __global__ void k_bounds(RbxPoints P, RbxCells C, double min_cell, BoundsWS *ws,
-                         uint32_t *status) {
+                         uint32_t *status, int32_t *counts, int nscan) {
   RBX_SKIP_IF_VALID(C);
+  // the cell histogram of k_count starts from zero: cleared here (only when
+  // the list is rebuilt) rather than by a memset of cap_cells words per step
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nscan; k += gridDim.x * blockDim.x)
+    counts[k] = 0;
   double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < P.n; k += gridDim.x * blockDim.x) {
     int g = P.index ? P.index[k] : k;
@@ -301,13 +305,12 @@ extern "C" int rbx_cells_build(const RbxPoints *pts, const RbxCells *cells, doub
 
   cudaMemsetAsync(bws->mn, 0xFF, sizeof(bws->mn), st);
   cudaMemsetAsync(bws->mx, 0x00, sizeof(bws->mx) + 2 * sizeof(unsigned int), st);
-  cudaMemsetAsync(counts, 0, sizeof(int32_t) * nscan, st);
 
   const int T = 256;
   int nb = rbx_blocks(pts->n, T);
   int bb = nb < 148 * 8 ? nb : 148 * 8;
   nb = nb < 148 * 16 ? nb : 148 * 16;     // grid-stride loops
-  k_bounds<<<bb, T, 0, st>>>(*pts, *cells, min_cell, bws, status);
+  k_bounds<<<bb, T, 0, st>>>(*pts, *cells, min_cell, bws, status, counts, nscan);
   k_count<<<nb, T, 0, st>>>(*pts, *cells, counts);
   k_scan_tiles<<<ntiles, kScanThreads, 0, st>>>(*cells, counts, cells->cell_start, tile_sum, nscan);
   k_scan_sums<<<1, 1024, 0, st>>>(*cells, tile_sum, ntiles);
