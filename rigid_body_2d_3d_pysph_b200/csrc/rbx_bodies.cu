@@ -1,7 +1,7 @@
-// Per-body kernels: force/torque reduction and the rigid steppers, plus the
-// per-particle pose kernel.  One warp per body for the reduction (lanes
-// stride over the body's particles, fixed shuffle tree => deterministic);
-// the 3x3 algebra of a body is done by lane 0 (a few hundred flops).
+// Per-body kernels: the force/torque reduction (k_reduce: one warp per body,
+// lanes stride over the body's particles, fixed shuffle tree => deterministic)
+// and the rigid steppers (k_bodies, k_rk2: one thread per body for the 3x3
+// algebra), plus the per-particle pose kernel and the multi-GPU halo payload.
 //
 //   SumUpExternalForces.reduce        rigid_body_common.py:128-175
 //   GTVFRigidBody3DStep.py_stage1/3   rigid_body_3d.py:41-60, 171-190

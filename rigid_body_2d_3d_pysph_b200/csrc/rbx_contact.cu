@@ -32,7 +32,7 @@
 //   5. finalize_slots: normals, distance, spring/dashpot/Coulomb law with the
 //      history carried in the sparse slot table, for the parked slots in
 //      ascending dem_id,
-//   6. writes fx, fy, fz; k_bodies (rbx_bodies.cu) sums them per body with a
+//   6. writes fx, fy, fz; k_reduce (rbx_bodies.cu) sums them per body with a
 //      fixed shuffle tree (deterministic).
 #include "rbx_common.cuh"
 #include <string.h>
@@ -769,7 +769,7 @@ k_slots(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
   __shared__ double acc[kAcc][kFields][kSlotsCta];
 
   // work item t <-> particle nbr_order[t] (k_list_sort): full warps of equal
-  // list length.  The per-body force/torque sum is done by k_bodies.
+  // list length.  The per-body force/torque sum is done by k_reduce.
   const int tid = threadIdx.x, lane = tid & 31;
   const size_t n_rigid = (size_t)S.n_rigid;
   unsigned nactive = 0, npairs = 0;
