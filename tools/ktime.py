@@ -1,6 +1,6 @@
 """time k_neighbours / k_slots separately on a settled pile"""
 import sys, ctypes, torch, numpy as np
-sys.path.insert(0,'/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from rigid_body_2d_3d_pysph_b200 import _lib
 from rigid_body_2d_3d_pysph_b200.device import DeviceScene
 from rigid_body_2d_3d_pysph_b200.scenes import synthetic_pile

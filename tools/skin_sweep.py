@@ -1,6 +1,6 @@
 """steady-state step time of the 10M pile as a function of the skin factor"""
 import sys, torch, numpy as np
-sys.path.insert(0,'/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from rigid_body_2d_3d_pysph_b200.device import DeviceScene
 from rigid_body_2d_3d_pysph_b200.scenes import synthetic_pile
 nb=int(sys.argv[1]); settle=int(sys.argv[2])

@@ -1,5 +1,5 @@
 import sys, torch, numpy as np, time
-sys.path.insert(0,'/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from rigid_body_2d_3d_pysph_b200.device import DeviceScene
 from rigid_body_2d_3d_pysph_b200.scenes import synthetic_pile
 nb=int(sys.argv[1]) if len(sys.argv)>1 else 100000
