@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RBX_VERSION 203 /* 0.2.3 */
+#define RBX_VERSION 300 /* 0.3.0 */
 
 typedef enum {
   RBX_OK = 0,
@@ -49,6 +49,7 @@ typedef enum {
 #define RBX_STATUS_LIST_OVERFLOW 4u  /* per-particle neighbour list full       */
 #define RBX_STATUS_GRID_COARSENED 8u /* cell size enlarged to fit cap_cells    */
 #define RBX_STATUS_LVC_OVERFLOW 16u  /* LVC tangential history `limit` hit     */
+#define RBX_STATUS_PAIR_OVERFLOW 32u /* RbxDiag.pairs buffer full              */
 
 #define RBX_MAX_KEYS 8   /* slots per particle the optional RbxDiag arrays hold */
 
@@ -165,6 +166,18 @@ typedef struct {
   uint32_t *rebuild;
   double *xcm_ref, *R_ref;    /* [3 n_bodies], [9 n_bodies] at last build */
   const double *rmax;         /* [n_bodies] max |body-frame position|     */
+  /* Two-precision contact evaluation (optional: both NULL -> every slot is
+   * evaluated in FP64).  pos32[n_total] = {x - origin[0], y - origin[1],
+   * z - origin[2], h} as floats, kept current by rbx_pose_particles (rigid
+   * particles), rbx_halo_unpack, rbx_pos32_refresh, and for the static
+   * particles by rbx_contact_neighbours on a rebuild.  A first pass sums
+   * every (particle, source body) slot in FP32 with a running error bound
+   * and proves most of them out of contact; clist[2 n_rigid] receives
+   * {work item, bit mask of the runs that could not be excluded} and only
+   * those are evaluated by the exact FP64 code.  counters[6] = entries.     */
+  float *pos32;
+  int32_t *clist;
+  double origin[3];
 } RbxScene;
 
 typedef struct {
@@ -176,7 +189,11 @@ typedef struct {
   double h_uniform; /* > 0: every particle has this h (skips the h loads)  */
   double skin;      /* >= 0: extra radius of the neighbour lists; 0 rebuilds
                        them at every evaluation                            */
+  int32_t flags;    /* RBX_PARAM_* */
+  int32_t pad_;
 } RbxParams;
+
+#define RBX_PARAM_EXACT 1  /* evaluate every slot in FP64 (no FP32 first pass) */
 
 /* Optional per-slot diagnostics of one contact evaluation, slot-major
  * [RBX_MAX_KEYS][n_rigid]; any pointer may be NULL.  Used by parity tests
@@ -185,6 +202,14 @@ typedef struct {
   int32_t *key;     /* source dem_id, -1 = unused                        */
   int32_t *closest; /* global index of the closest source particle       */
   double *nx, *ny, *nz, *dist, *overlap, *ftx, *fty, *ftz;
+  /* neighbour pairs as the contact kernel sees them: every list entry that
+   * passes the gate of rigid_body_common.py:678-679 and the exact NNPS
+   * predicate is appended as {destination, source} (global indices, in no
+   * particular order) to pairs[2 pair_cap]; pair_count[0] = pairs found
+   * (may exceed pair_cap: RBX_STATUS_PAIR_OVERFLOW).  NULL: not wanted.   */
+  int32_t *pairs;
+  unsigned long long *pair_count;
+  int64_t pair_cap;
 } RbxDiag;
 
 /* The DEMScheme scene (dem.py): granular (destination) particles first,
@@ -296,6 +321,11 @@ int rbx_gtvf_drift(const RbxScene *scene, double dt, double skin,
 #define RBX_POSE_VEL_PREV 4  /* velocities use R_prev (stage1 fused after drift) */
 #define RBX_POSE_NORMALS 8   /* rotate normal0 -> normal where is_boundary */
 int rbx_pose_particles(const RbxScene *scene, int flags, void *stream);
+
+/* pos32 of the particles [first, first + n) from x, y, z, h (after the caller
+ * wrote positions itself; no counterpart in the reference).                 */
+int rbx_pos32_refresh(const RbxScene *scene, int32_t first, int32_t n,
+                      void *stream);
 
 /* Multi-GPU halo payload (no counterpart in the reference, which is single
  * process): rows of 8 doubles {x, y, z, u, v, w, h, dem_id}.  pack gathers

@@ -18,10 +18,10 @@ _lib = None
 
 
 def build(force=False):
-    """gcc -O2 -fopenmp -ffp-contract=off."""
+    """gcc -O3 -fopenmp -ffp-contract=off."""
     if force or not os.path.exists(_SO) or \
             os.path.getmtime(_SO) < os.path.getmtime(_SRC):
-        cmd = ['gcc', '-O2', '-fopenmp', '-ffp-contract=off', '-fPIC',
+        cmd = ['gcc', '-O3', '-fopenmp', '-ffp-contract=off', '-fPIC',
                '-shared', '-std=c99', '-o', _SO, _SRC, '-lm']
         subprocess.check_call(cmd)
     return _SO

@@ -19,6 +19,8 @@ STATUS_HIST_OVERFLOW = 2
 STATUS_LIST_OVERFLOW = 4
 STATUS_GRID_COARSENED = 8
 STATUS_LVC_OVERFLOW = 16
+STATUS_PAIR_OVERFLOW = 32
+PARAM_EXACT = 1
 
 POSE_POS, POSE_VEL, POSE_VEL_PREV, POSE_NORMALS = 1, 2, 4, 8
 
@@ -53,12 +55,12 @@ _SCENE_PTRS = ['x', 'y', 'z', 'u', 'v', 'w', 'h', 'm', 'rho', 'dem_id',
                'iinv_g', 'xcm0', 'vcm0', 'ang_mom0', 'R0', 'eta', 'eta_row',
                'hist_key_in', 'hist_dlt_in', 'hist_fn_in', 'hist_key_out',
                'hist_dlt_out', 'hist_fn_out', 'status', 'counters', 'rebuild',
-               'xcm_ref', 'R_ref', 'rmax']
+               'xcm_ref', 'R_ref', 'rmax', 'pos32', 'clist']
 
 
 class RbxScene(ctypes.Structure):
     _fields_ = [(n, c_i32) for n in _SCENE_INTS] + \
-               [(n, c_vp) for n in _SCENE_PTRS]
+               [(n, c_vp) for n in _SCENE_PTRS] + [('origin', c_f64 * 3)]
 
 
 _DEM_PTRS = ['x', 'y', 'z', 'u', 'v', 'w', 'wx', 'wy', 'wz', 'h', 'm', 'rad_s',
@@ -78,7 +80,8 @@ class RbxParams(ctypes.Structure):
     _fields_ = [('radius_scale', c_f64), ('kr', c_f64), ('kf', c_f64),
                 ('fric_coeff', c_f64), ('gx', c_f64), ('gy', c_f64),
                 ('gz', c_f64), ('dt', c_f64), ('reach', c_f64),
-                ('h_uniform', c_f64), ('skin', c_f64)]
+                ('h_uniform', c_f64), ('skin', c_f64), ('flags', c_i32),
+                ('pad_', c_i32)]
 
 
 class RbxCanelas(ctypes.Structure):
@@ -89,7 +92,8 @@ class RbxCanelas(ctypes.Structure):
 class RbxDiag(ctypes.Structure):
     _fields_ = [('key', c_vp), ('closest', c_vp), ('nx', c_vp), ('ny', c_vp),
                 ('nz', c_vp), ('dist', c_vp), ('overlap', c_vp),
-                ('ftx', c_vp), ('fty', c_vp), ('ftz', c_vp)]
+                ('ftx', c_vp), ('fty', c_vp), ('ftz', c_vp), ('pairs', c_vp),
+                ('pair_count', c_vp), ('pair_cap', c_i64)]
 
 
 # every symbol include/rbx.h declares
@@ -97,7 +101,8 @@ SYMBOLS = ['rbx_version', 'rbx_strerror', 'rbx_sizeof',
            'rbx_cells_workspace_bytes', 'rbx_cells_build', 'rbx_pairs_dump',
            'rbx_contact_mofidi', 'rbx_contact_neighbours',
            'rbx_contact_slots', 'rbx_contact_canelas', 'rbx_reduce_bodies', 'rbx_gtvf_kick',
-           'rbx_gtvf_drift', 'rbx_pose_particles', 'rbx_halo_pack',
+           'rbx_gtvf_drift', 'rbx_pose_particles', 'rbx_pos32_refresh',
+           'rbx_halo_pack',
            'rbx_halo_unpack', 'rbx_rk2_stage',
            'rbx_gtvf_step', 'rbx_contact_lvc', 'rbx_dem_step',
            'rbx_boundary_identify']
@@ -147,6 +152,7 @@ def load():
     L.rbx_gtvf_kick.argtypes = [P(RbxScene), c_f64, c_vp]
     L.rbx_gtvf_drift.argtypes = [P(RbxScene), c_f64, c_f64, c_vp]
     L.rbx_pose_particles.argtypes = [P(RbxScene), ctypes.c_int, c_vp]
+    L.rbx_pos32_refresh.argtypes = [P(RbxScene), c_i32, c_i32, c_vp]
     L.rbx_halo_pack.argtypes = [P(RbxScene), c_vp, c_i32, c_vp, c_vp]
     L.rbx_halo_unpack.argtypes = [P(RbxScene), c_i32, c_i32, c_vp, c_vp]
     L.rbx_rk2_stage.argtypes = [P(RbxScene), ctypes.c_int, c_f64,

@@ -232,9 +232,15 @@ __global__ void k_pose(RbxScene S, int flags) {
     const double dx = (R[0] * x0 + R[1] * y0 + R[2] * z0);
     const double dy = (R[3] * x0 + R[4] * y0 + R[5] * z0);
     const double dz = (R[6] * x0 + R[7] * y0 + R[8] * z0);
-    S.x[p] = S.xcm[i3] + dx;
-    S.y[p] = S.xcm[i3 + 1] + dy;
-    S.z[p] = S.xcm[i3 + 2] + dz;
+    const double xn = S.xcm[i3] + dx, yn = S.xcm[i3 + 1] + dy, zn = S.xcm[i3 + 2] + dz;
+    S.x[p] = xn;
+    S.y[p] = yn;
+    S.z[p] = zn;
+    // FP32 copy for the first pass of the contact evaluation (k_filter)
+    if (S.pos32)
+      reinterpret_cast<float4 *>(S.pos32)[p] =
+          make_float4((float)(xn - S.origin[0]), (float)(yn - S.origin[1]),
+                      (float)(zn - S.origin[2]), (float)S.h[p]);
     if ((flags & RBX_POSE_NORMALS) && S.normal && S.is_boundary && S.is_boundary[p] == 1) {
       const double n0 = S.normal0[3 * p], n1 = S.normal0[3 * p + 1], n2 = S.normal0[3 * p + 2];
       S.normal[3 * p] = (R[0] * n0 + R[1] * n1 + R[2] * n2);
@@ -261,6 +267,12 @@ __global__ void k_halo_unpack(RbxScene S, int first, int n, const double *rows) 
   double *col[7] = {S.x, S.y, S.z, S.u, S.v, S.w, const_cast<double *>(S.h)};
   if (c < 7) col[c][q] = rows[k];
   else const_cast<int32_t *>(S.dem_id)[q] = (int32_t)rows[k];
+  if (c == 0 && S.pos32) {
+    const double *r = rows + (size_t)(k >> 3) * 8;
+    reinterpret_cast<float4 *>(S.pos32)[q] =
+        make_float4((float)(r[0] - S.origin[0]), (float)(r[1] - S.origin[1]),
+                    (float)(r[2] - S.origin[2]), (float)r[6]);
+  }
 }
 
 int launch_bodies(const RbxScene *S, int mode, double dt, double skin, cudaStream_t st) {

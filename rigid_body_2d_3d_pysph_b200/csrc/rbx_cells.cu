@@ -308,8 +308,9 @@ extern "C" int rbx_cells_build(const RbxPoints *pts, const RbxCells *cells, doub
 
   const int T = 256;
   int nb = rbx_blocks(pts->n, T);
-  int bb = nb < 148 * 8 ? nb : 148 * 8;
-  nb = nb < 148 * 16 ? nb : 148 * 16;     // grid-stride loops
+  const int sms = rbx_sm_count();
+  int bb = nb < sms * 8 ? nb : sms * 8;
+  nb = nb < sms * 16 ? nb : sms * 16;     // grid-stride loops
   k_bounds<<<bb, T, 0, st>>>(*pts, *cells, min_cell, bws, status, counts, nscan);
   k_count<<<nb, T, 0, st>>>(*pts, *cells, counts);
   k_scan_tiles<<<ntiles, kScanThreads, 0, st>>>(*cells, counts, cells->cell_start, tile_sum, nscan);
@@ -318,7 +319,7 @@ extern "C" int rbx_cells_build(const RbxPoints *pts, const RbxCells *cells, doub
   k_scatter<<<nb, T, 0, st>>>(*pts, *cells);
   {
     int ns = rbx_blocks(cells->cap_cells, T);
-    k_sort_cells<<<ns < 148 * 16 ? ns : 148 * 16, T, 0, st>>>(*cells);
+    k_sort_cells<<<ns < sms * 16 ? ns : sms * 16, T, 0, st>>>(*cells);
   }
   k_gather<<<nb, T, 0, st>>>(*pts, *cells);
   RBX_CHECK_LAUNCH();

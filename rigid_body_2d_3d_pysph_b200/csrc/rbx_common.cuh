@@ -21,6 +21,21 @@ static inline int rbx_blocks(long long n, int threads) {
   return (int)(b < 1 ? 1 : b);
 }
 
+// SMs of the current device (launch geometry of the persistent kernels);
+// a device attribute, cached per device.
+static inline int rbx_sm_count() {
+  static int cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cache[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+    cache[dev] = n;
+  }
+  return cache[dev];
+}
+
 // ---- ordered-uint64 encoding of doubles, for atomicMin/atomicMax ----
 __device__ __forceinline__ unsigned long long rbx_ord(double v) {
   unsigned long long b = (unsigned long long)__double_as_longlong(v);

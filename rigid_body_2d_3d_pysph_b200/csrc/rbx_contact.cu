@@ -760,7 +760,12 @@ park_overflow(double (*ovf)[kFields], int nk, double ax, double ay, double az, d
   return nk + 1;
 }
 
-template <int DIM, bool UNIFORM_H>
+// One work item = one particle and the runs of its list that have to be
+// evaluated exactly.  clist == nullptr: every particle, every run (the
+// reference semantics in one pass; diagnostics, pair dump).  Otherwise item i
+// of the compact list written by k_filter: {work item t, bit mask of the runs
+// that the FP32 pass could not exclude (bit 31 = run 31 and every later one)}.
+template <int DIM, bool UNIFORM_H, bool COMPACT>
 __global__ void __launch_bounds__(kSlotsCta, RBX_SLOTS_MINB)
 k_slots(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
         const __grid_constant__ RbxDiag D, double h_uniform) {
@@ -779,27 +784,33 @@ k_slots(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
   // multiple of the 8 warps of a sort window would give a CTA the same length
   // class every time).  A finished warp takes its next block at once instead
   // of waiting for a CTA launch.
-  const int nitems = (S.n_rigid + kSlotsCta - 1) / kSlotsCta;
+  const int nwork = COMPACT ? (int)S.counters[6] : S.n_rigid;
+  const int nitems = (nwork + kSlotsCta - 1) / kSlotsCta;
   // particle and list length of the work item after this one: loaded a whole
   // item ahead, so that its particle data and first list rows can be pulled
   // into L2 while this item finishes (a warp otherwise starts every item with
   // three dependent DRAM round trips and nothing to overlap them with)
-  int p_next = -1, cnt_next = 0;
-  {
-    const int t0 = blockIdx.x * kSlotsCta + tid;
-    if (t0 < S.n_rigid) { p_next = S.nbr_order[t0]; cnt_next = S.nbr_cnt_srt[t0]; }
-  }
+  int p_next = -1, cnt_next = 0, t_next = 0;
+  unsigned mask_next = 0xffffffffu;
+  auto fetch_item = [&](int i) {
+    p_next = -1;
+    if (i < nwork) {
+      t_next = i;
+      if (COMPACT) { t_next = S.clist[2 * i]; mask_next = (unsigned)S.clist[2 * i + 1]; }
+      p_next = S.nbr_order[t_next];
+      cnt_next = S.nbr_cnt_srt[t_next];
+    }
+  };
+  fetch_item(blockIdx.x * kSlotsCta + tid);
   for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-  const int t = item * kSlotsCta + tid;
-  const bool valid = t < S.n_rigid;
+  const int t = t_next;
+  const bool valid = p_next >= 0;
   const int p = p_next;
   const int cnt_raw = cnt_next;
-  const int tn = t + gridDim.x * kSlotsCta;
-  p_next = -1;
-  if (item + gridDim.x < nitems && tn < S.n_rigid) {
-    p_next = S.nbr_order[tn];
-    cnt_next = S.nbr_cnt_srt[tn];
-  }
+  const unsigned run_mask = mask_next;
+  if (item + gridDim.x < nitems) fetch_item((item + gridDim.x) * kSlotsCta + tid);
+  else p_next = -1;
+  const int tn = t_next;
   if (valid) {
     const int nlist = cnt_raw & (kSplitBit - 1);
     // partial slots of a split body and the slots of a diagnostics run are
@@ -821,6 +832,7 @@ k_slots(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
     int qmin = -1;           // its global index
     bool touched = false;    // some entry passed the neighbour predicate
     int nk = 0;              // slots parked in shared memory
+    int run = 0;             // ordinal of the source-body run being read
     SlotOut so;
     so.cfx = so.cfy = so.cfz = 0.;
     so.nout = 0; so.ki = 0; so.st = 0u; so.nactive = 0u;
@@ -892,6 +904,11 @@ k_slots(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
       if (in) {
         npairs++;
         touched = true;
+        if (D.pairs) {                 // parity mode: the pair set as seen here
+          const unsigned long long k2 = atomicAdd(D.pair_count, 1ull);
+          if ((long long)k2 < D.pair_cap) { D.pairs[2 * k2] = p; D.pairs[2 * k2 + 1] = qi; }
+          else so.st |= RBX_STATUS_PAIR_OVERFLOW;
+        }
         // :811 closest source (+ tie rule Q6).  The reference compares
         // correctly rounded distances; a squared distance smaller by more
         // than a few ulp decides the same way without the square roots,
@@ -921,6 +938,10 @@ k_slots(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
         r2thr = rmin0 * rmin0; qmin = -1; touched = false;
       }
     };
+    // COMPACT: is the run with this ordinal one of those to evaluate?
+    auto selected = [&](int r) -> bool {
+      return !COMPACT || ((run_mask >> (r < 31 ? r : 31)) & 1u) != 0u;
+    };
 #pragma unroll 2
     for (int e0 = 0; e0 < nlist; e0 += 2) {
       // stage G for entries e0 + 2, e0 + 3; stage L for e0 + 2 + kLd, + 3 + kLd
@@ -935,12 +956,20 @@ k_slots(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
       ql[kLd - 2] = (e0 + 2 + kLd < nlist) ? cl[0] : 0;
       ql[kLd - 1] = (e0 + 3 + kLd < nlist) ? cl[n_rigid] : 0;
       cl += 2 * n_rigid;
-      double a0, a1, a2, ar, at1, at2, b0, b1, b2, br, bt1, bt2;
-      bool ain, bin;
-      pair_math(c0x, c0y, c0z, c0h, a0, a1, a2, ar, at1, at2, ain);
-      pair_math(c1x, c1y, c1z, c1h, b0, b1, b2, br, bt1, bt2, bin);
-      add_pair(qc0, a0, a1, a2, ar, at1, at2, ain);
-      if (e0 + 1 < nlist) add_pair(qc1, b0, b1, b2, br, bt1, bt2, bin);
+      // runs the FP32 pass has excluded are only stepped over (an excluded
+      // slot adds exactly nothing: rigid_body_common.py:1014-1027)
+      const bool s0 = selected(run);
+      const int run1 = run + (qc0 < 0 ? 1 : 0);
+      const bool s1 = e0 + 1 < nlist && selected(run1);
+      if (s0 || s1) {
+        double a0, a1, a2, ar, at1, at2, b0, b1, b2, br, bt1, bt2;
+        bool ain, bin;
+        pair_math(c0x, c0y, c0z, c0h, a0, a1, a2, ar, at1, at2, ain);
+        pair_math(c1x, c1y, c1z, c1h, b0, b1, b2, br, bt1, bt2, bin);
+        if (s0) add_pair(qc0, a0, a1, a2, ar, at1, at2, ain);
+        if (s1) add_pair(qc1, b0, b1, b2, br, bt1, bt2, bin);
+      }
+      run = run1 + ((e0 + 1 < nlist && qc1 < 0) ? 1 : 0);
       qc0 = qn0; c0x = g0x; c0y = g0y; c0z = g0z; c0h = g0h;
       qc1 = qn1; c1x = g1x; c1y = g1y; c1z = g1z; c1h = g1h;
     }
@@ -973,7 +1002,194 @@ k_slots(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
       np_ += __shfl_xor_sync(0xffffffffu, np_, o);
     }
     if (lane == 0 && na) atomicAdd(&S.counters[1], (unsigned long long)na);
-    if (lane == 0 && np_) atomicAdd(&S.counters[0], (unsigned long long)np_);
+    // (COMPACT: the FP32 pass has counted the pairs of every run)
+    if (!COMPACT && lane == 0 && np_) atomicAdd(&S.counters[0], (unsigned long long)np_);
+  }
+}
+
+
+// ---- FP32 first pass ---------------------------------------------------------
+// At config 5 fewer than 1 % of the (particle, source body) slots are in
+// contact, but deciding that takes the slot's complete sums.  k_filter forms
+// the same sums as k_slots in FP32 (positions relative to RbxScene.origin,
+// one 16-byte gather per entry, twice the issue rate and half the registers of
+// FP64) together with a RUNNING BOUND of their error, and drops a slot only if
+// the contact condition of rigid_body_common.py:906-907,
+//     overlap = spacing0 - dist > 0,   dist = (A . B) / (|A| w)
+// (A = sum XIJ m/(rho r) W, B = sum XIJ m/rho W, w = sum m/rho W), fails for
+// EVERY value the exact sums can have inside the bound.  What cannot be
+// excluded is evaluated by the unchanged FP64 code (k_slots<COMPACT>), so the
+// results are those of the one-pass FP64 evaluation bit for bit
+// (tests/test_gpu_fast.py); a dropped slot contributes exactly nothing, as
+// the zeroed slot of the reference's else branch (:1014-1027).
+//
+// Error model (u = 2^-24, E = largest |coordinate - origin| of the particle or
+// any list neighbour, L = list radius, all per component):
+//   stored coordinate      |d| <= u E         ->  XIJ:  ex = 2.1 u E
+//   r (FMA sum, MUFU.RSQ)  er = sqrt(3) ex + 4 u L;   q = r / h:  er / h
+//   W = T w(q):            |dW| <= T |w'(q)| er / h + (second order) + 9 u W,
+//                          |w'| <= D = 5 t3^4 + 30 t2^4 + 75 t1^4
+//   XIJ / r:               (ex + er) / r
+// so with the extra sums  SD = sum (T / h) (D + floor),  wA = sum tmp1:
+//   dw = er SD + cu w,   dA = sqrt3 ((ex + er) wA + dw),
+//   dB = sqrt3 (ex w + L dw),   cu = (list_cap + 16) u  (accumulation).
+// No contact is certain when
+//   A.B - [w dB + L w dA + dA dB] > spacing0 (|A| + dA) (w + dw)
+// (|A| <= w, |B| <= L w), tested on squares; NaN (coincident points) fails the
+// test and is kept.  Runs past ordinal 30 share mask bit 31.
+#ifndef RBX_FILTER_MINB
+#define RBX_FILTER_MINB 32
+#endif
+
+template <int DIM, bool UNIFORM_H>
+__global__ void __launch_bounds__(32, RBX_FILTER_MINB)
+k_filter(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
+         float h_uniform) {
+  const int lane = threadIdx.x;
+  const size_t n_rigid = (size_t)S.n_rigid;
+  const float4 *__restrict__ pos = reinterpret_cast<const float4 *>(S.pos32);
+  const int nitems = (S.n_rigid + 31) / 32;
+  unsigned npairs = 0;
+  constexpr float kU = 5.9604645e-8f;            // 2^-24
+  constexpr float kSqrt3 = 1.7320509f;
+  const float Lr = (float)((P.reach + P.skin) * (1. + 1e-6));
+  const float cu = (float)(S.list_cap + 16) * kU;
+  const float sigma = DIM == 2 ? (float)(0.31830988618379067154 * 7.0 / 478.0)
+                               : (float)(0.31830988618379067154 / 120.0);
+
+  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int t = item * 32 + lane;
+    const bool valid = t < S.n_rigid;
+    unsigned mask = 0u;
+    if (valid) {
+      const int p = S.nbr_order[t];
+      const int cnt_raw = S.nbr_cnt_srt[t];
+      const int nlist = cnt_raw & (kSplitBit - 1);
+      const bool all = (cnt_raw & kSplitBit) != 0;   // split bodies: partial sums
+      const float4 me = pos[p];
+      const float s0 = (float)S.spacing0[S.body[p]];
+      const float vol = (float)(S.m[p] / S.rho[p]);
+      // error coefficients of this particle
+      const float E = fmaxf(fmaxf(fabsf(me.x), fabsf(me.y)), fabsf(me.z)) + Lr;
+      const float ex = 2.1f * kU * E;
+      const float er = kSqrt3 * ex + 4.f * kU * Lr;
+      const float eu = ex + er;
+      const float s0sq = s0 * s0 * 1.0001f;
+      // uniform h: constants of the kernel
+      float h1 = 0.f, Th = 0.f, T = 0.f, dfloor = 0.f;
+      if (UNIFORM_H) {
+        h1 = 1.f / (0.5f * (me.w + h_uniform));
+        T = vol * sigma * (DIM == 2 ? h1 * h1 : h1 * h1 * h1);
+        Th = T * h1;
+        dfloor = 300.f * er * h1;
+      }
+
+      float ax = 0.f, ay = 0.f, az = 0.f, w1 = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
+      float wA = 0.f, SD = 0.f;
+      int run = 0;
+
+      auto entry = [&](int qc, const float4 sp) {
+        const float dx = me.x - sp.x, dy = me.y - sp.y, dz = me.z - sp.z;
+        const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        float rinv;
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(r2));
+        const float r = r2 * rinv;
+        if (!UNIFORM_H) {
+          float hij = 0.5f * (me.w + sp.w);
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(h1) : "f"(hij));
+          T = vol * sigma * (DIM == 2 ? h1 * h1 : h1 * h1 * h1);
+          Th = T * h1;
+          dfloor = 300.f * er * h1;
+        }
+        const float q = r * h1;
+        const float t3 = fmaxf(3.f - q, 0.f), t2 = fmaxf(2.f - q, 0.f), t1 = fmaxf(1.f - q, 0.f);
+        const float a3 = t3 * t3, a2 = t2 * t2, a1 = t1 * t1;
+        const float b3 = a3 * a3, b2 = a2 * a2, b1 = a1 * a1;
+        const float wv = fmaf(15.f, b1 * t1, fmaf(-6.f, b2 * t2, b3 * t3));
+        const float Dq = fmaf(75.f, b1, fmaf(30.f, b2, fmaf(5.f, b3, dfloor)));
+        const float tmp2 = T * wv;
+        const float tmp1 = tmp2 * rinv;
+        ax = fmaf(dx, tmp1, ax); ay = fmaf(dy, tmp1, ay); az = fmaf(dz, tmp1, az);
+        bx = fmaf(dx, tmp2, bx); by = fmaf(dy, tmp2, by); bz = fmaf(dz, tmp2, bz);
+        w1 += tmp2;
+        wA += tmp1;
+        // entries beyond the support add their floor only (D = 0 there, but
+        // the rounded q may sit on the other side of 3)
+        SD = fmaf(Th, Dq, SD);
+        if (t3 > 0.f) npairs++;
+        if (qc < 0) {                              // last entry of a source body
+          const float dw = fmaf(er, SD, cu * w1);
+          const float dA = kSqrt3 * fmaf(eu, wA, dw);
+          const float dB = kSqrt3 * fmaf(ex, w1, Lr * dw);
+          const float ab = fmaf(az, bz, fmaf(ay, by, ax * bx));
+          const float aa = fmaf(az, az, fmaf(ay, ay, ax * ax));
+          const float eab = 1.01f * fmaf(dA, dB, w1 * fmaf(Lr, dA, dB));
+          const float lhs = ab - eab;
+          const float aahi = fmaf(dA, fmaf(2.f, w1, dA), aa);
+          const float wh = w1 + dw;
+          const float rhs = s0sq * (wh * wh) * aahi;
+          // w <= 1e-12: the slot has no normal, dist = 0, overlap == spacing0
+          const bool drop = (wh < 0.99e-12f) || (lhs > 0.f && lhs * lhs > rhs);
+          if (!drop || all) mask |= 1u << (run < 31 ? run : 31);
+          run++;
+          ax = ay = az = w1 = bx = by = bz = 0.f;
+          wA = SD = 0.f;
+        }
+      };
+
+      // software pipeline: the list entries of the next pair of entries are
+      // in flight while the positions of this one are gathered
+      const int *cl = S.nbr_srt + t;
+      int qa = nlist > 0 ? cl[0] : 0;
+      int qb = nlist > 1 ? cl[n_rigid] : 0;
+      int la = nlist > 2 ? cl[2 * n_rigid] : 0;
+      int lb = nlist > 3 ? cl[3 * n_rigid] : 0;
+      cl += 4 * n_rigid;
+      float4 sa = pos[qa & 0x7fffffff], sb = pos[qb & 0x7fffffff];
+      for (int e0 = 0; e0 < nlist; e0 += 2) {
+        const float4 ga = pos[la & 0x7fffffff], gb = pos[lb & 0x7fffffff];
+        const int na = (e0 + 4 < nlist) ? cl[0] : 0;
+        const int nb = (e0 + 5 < nlist) ? cl[n_rigid] : 0;
+        cl += 2 * n_rigid;
+        entry(qa, sa);
+        if (e0 + 1 < nlist) entry(qb, sb);
+        qa = la; qb = lb; sa = ga; sb = gb; la = na; lb = nb;
+      }
+      if (mask == 0u) {
+        // nothing can be in contact: BodyForce alone (:122-125), no history
+        const double md = S.m[p];
+        S.fx[p] = md * P.gx; S.fy[p] = md * P.gy; S.fz[p] = md * P.gz;
+        S.hist_key_out[p] = -1;
+      }
+    }
+    // the rest goes to the exact pass: {work item, run mask}, appended in
+    // lane order (which block of the list a warp gets does not matter)
+    const unsigned bal = __ballot_sync(0xffffffffu, mask != 0u);
+    if (bal) {
+      int base = 0;
+      if (lane == 0) base = (int)atomicAdd(&S.counters[6], (unsigned long long)__popc(bal));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (mask != 0u) {
+        const int k = base + __popc(bal & ((1u << lane) - 1u));
+        S.clist[2 * k] = t;
+        S.clist[2 * k + 1] = (int)mask;
+      }
+    }
+  }
+  unsigned np_ = npairs;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) np_ += __shfl_xor_sync(0xffffffffu, np_, o);
+  if (lane == 0 && np_) atomicAdd(&S.counters[0], (unsigned long long)np_);
+}
+
+// pos32 of the particles [first, first + n)
+__global__ void k_pos32(RbxScene S, int first, int n, int only_on_rebuild) {
+  if (only_on_rebuild && S.rebuild && *S.rebuild == 0u) return;
+  float4 *pos = reinterpret_cast<float4 *>(S.pos32);
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const int q = first + k;
+    pos[q] = make_float4((float)(S.x[q] - S.origin[0]), (float)(S.y[q] - S.origin[1]),
+                         (float)(S.z[q] - S.origin[2]), (float)S.h[q]);
   }
 }
 
@@ -997,13 +1213,32 @@ extern "C" int rbx_contact_neighbours(const RbxScene *scene, const RbxCells *cel
   const int nb = scene->n_chunks;
   if (params->skin < 0.) return RBX_ERR_INVALID;
   {
-    const int grid = nb < 148 * RBX_NB_MINB * 4 ? nb : 148 * RBX_NB_MINB * 4;
+    const int cap = rbx_sm_count() * RBX_NB_MINB * 4;
+    const int grid = nb < cap ? nb : cap;
     k_neighbours<<<grid, RBX_CHUNK, 0, st>>>(*scene, *cells, *params, params->reach + params->skin);
+  }
+  // FP32 positions of the static particles (walls, halo): whoever moves
+  // them raises the rebuild flag
+  if (scene->pos32 && scene->n_total > scene->n_rigid) {
+    const int n = scene->n_total - scene->n_rigid;
+    const int nbp = rbx_blocks(n, 256), capp = rbx_sm_count() * 8;
+    k_pos32<<<nbp < capp ? nbp : capp, 256, 0, st>>>(*scene, scene->n_rigid, n, 1);
   }
   k_list_sort<<<rbx_blocks(scene->n_rigid, kSortW), kSortW, 0, st>>>(*scene);
   if (scene->rebuild)
     k_list_commit<<<rbx_blocks(scene->n_bodies, 256), 256, 0, st>>>(*scene);
   k_list_clear<<<1, 1, 0, st>>>(*scene, params->skin);
+  RBX_CHECK_LAUNCH();
+  return RBX_OK;
+}
+
+extern "C" int rbx_pos32_refresh(const RbxScene *scene, int32_t first, int32_t n,
+                                 void *stream_) {
+  if (!scene || first < 0 || n < 0 || (long long)first + n > scene->n_total) return RBX_ERR_INVALID;
+  if (!scene->pos32 || n == 0) return RBX_OK;
+  int nb = rbx_blocks(n, 256);
+  const int cap = rbx_sm_count() * 16;
+  k_pos32<<<nb < cap ? nb : cap, 256, 0, (cudaStream_t)stream_>>>(*scene, first, n, 0);
   RBX_CHECK_LAUNCH();
   return RBX_OK;
 }
@@ -1016,17 +1251,43 @@ extern "C" int rbx_contact_slots(const RbxScene *scene, const RbxCells *cells,
   cudaStream_t st = (cudaStream_t)stream_;
   RbxDiag d;
   if (diag) d = *diag; else memset(&d, 0, sizeof(d));
+  if (d.pairs && (!d.pair_count || d.pair_cap < 0)) return RBX_ERR_INVALID;
   const bool uni = params->h_uniform > 0.;
-  // all CTAs resident at once (RBX_SLOTS_MINB per SM on 148 SMs), odd count
+  const int sms = rbx_sm_count();
+  // two-precision evaluation unless the caller asks for the one-pass FP64
+  // evaluation, wants per-slot diagnostics, or has no FP32 positions
+  const bool fast = scene->pos32 && scene->clist && !(params->flags & RBX_PARAM_EXACT) &&
+                    !d.key && !d.pairs && scene->list_cap < (1 << 20);
+  // all CTAs resident at once (RBX_SLOTS_MINB per SM), odd count
   int ng = rbx_blocks(scene->n_rigid, kSlotsCta);
-  const int resident = 148 * RBX_SLOTS_MINB - 1;
+  const int resident = sms * RBX_SLOTS_MINB - 1;
   if (ng > resident) ng = resident;
-  if (scene->dim == 3) {
-    if (uni) k_slots<3, true><<<ng, kSlotsCta, 0, st>>>(*scene, *params, d, params->h_uniform);
-    else k_slots<3, false><<<ng, kSlotsCta, 0, st>>>(*scene, *params, d, 0.);
+  if (fast) {
+    cudaMemsetAsync(&scene->counters[6], 0, sizeof(unsigned long long), st);
+    int nf = rbx_blocks(scene->n_rigid, 32);
+    const int resf = sms * RBX_FILTER_MINB - 1;
+    if (nf > resf) nf = resf;
+    const float hu = (float)params->h_uniform;
+    if (scene->dim == 3) {
+      if (uni) k_filter<3, true><<<nf, 32, 0, st>>>(*scene, *params, hu);
+      else k_filter<3, false><<<nf, 32, 0, st>>>(*scene, *params, 0.f);
+    } else {
+      if (uni) k_filter<2, true><<<nf, 32, 0, st>>>(*scene, *params, hu);
+      else k_filter<2, false><<<nf, 32, 0, st>>>(*scene, *params, 0.f);
+    }
+    if (scene->dim == 3) {
+      if (uni) k_slots<3, true, true><<<ng, kSlotsCta, 0, st>>>(*scene, *params, d, params->h_uniform);
+      else k_slots<3, false, true><<<ng, kSlotsCta, 0, st>>>(*scene, *params, d, 0.);
+    } else {
+      if (uni) k_slots<2, true, true><<<ng, kSlotsCta, 0, st>>>(*scene, *params, d, params->h_uniform);
+      else k_slots<2, false, true><<<ng, kSlotsCta, 0, st>>>(*scene, *params, d, 0.);
+    }
+  } else if (scene->dim == 3) {
+    if (uni) k_slots<3, true, false><<<ng, kSlotsCta, 0, st>>>(*scene, *params, d, params->h_uniform);
+    else k_slots<3, false, false><<<ng, kSlotsCta, 0, st>>>(*scene, *params, d, 0.);
   } else {
-    if (uni) k_slots<2, true><<<ng, kSlotsCta, 0, st>>>(*scene, *params, d, params->h_uniform);
-    else k_slots<2, false><<<ng, kSlotsCta, 0, st>>>(*scene, *params, d, 0.);
+    if (uni) k_slots<2, true, false><<<ng, kSlotsCta, 0, st>>>(*scene, *params, d, params->h_uniform);
+    else k_slots<2, false, false><<<ng, kSlotsCta, 0, st>>>(*scene, *params, d, 0.);
   }
   RBX_CHECK_LAUNCH();
   return RBX_OK;

@@ -54,7 +54,8 @@ class DeviceScene(object):
     def __init__(self, arrays, rigid_names, boundary_names=(), dim=3,
                  kr=1e5, kf=1e3, fric_coeff=0.5, gx=0., gy=0., gz=0.,
                  planar=False, ks=8, radius_scale=3.0, eta_uniform=None,
-                 cap_cells=None, list_cap=96, skin_factor=0.05, device=None):
+                 cap_cells=None, list_cap=96, skin_factor=0.05, device=None,
+                 exact=False):
         if not torch.cuda.is_available():
             raise _lib.RbxError('DeviceScene needs a CUDA device; the '
                                 'rigid-body path has no CPU fallback')
@@ -78,6 +79,10 @@ class DeviceScene(object):
             float(fric_coeff)
         self.g = (float(gx), float(gy), float(gz))
         self.eta_uniform = eta_uniform
+        # exact=True: every (particle, source body) slot is evaluated in FP64
+        # in one pass (RBX_PARAM_EXACT); default: FP32 first pass with an
+        # error bound, FP64 for what it cannot exclude -- identical results
+        self.exact = bool(exact)
         self._cap_cells_req = cap_cells
         self.parity = 0          # history ping-pong
         self.steps_done = 0
@@ -215,6 +220,16 @@ class DeviceScene(object):
                                         device=dev)
         self.T['nbr_order'] = torch.arange(nr_, dtype=i32, device=dev)
         self.T['nbr_cnt_srt'] = torch.zeros(nr_, dtype=i32, device=dev)
+        # two-precision contact evaluation: FP32 positions relative to the
+        # centre of the scene and the compact list of the exact pass
+        self.T['pos32'] = torch.zeros(4 * max(self.n_total, 1),
+                                      dtype=torch.float32, device=dev)
+        self.T['clist'] = torch.zeros(2 * nr_, dtype=i32, device=dev)
+        self.origin = [0., 0., 0.]
+        if self.n_total:
+            for k, n in enumerate('xyz'):
+                self.origin[k] = 0.5 * float((self.P[n].min() +
+                                              self.P[n].max()).item())
         # ---- damping table ---------------------------------------------
         self.eta_mode = 0
         self.T['eta'] = None
@@ -314,8 +329,10 @@ class DeviceScene(object):
         s.list_cap = self.list_cap
         for n in ['chunk_start', 'chunk_body', 'body_chunk', 'nbr_pos',
                   'nbr_cnt', 'nbr_srt', 'nbr_order', 'nbr_cnt_srt',
-                  'eta', 'eta_row']:
+                  'eta', 'eta_row', 'pos32', 'clist']:
             setattr(s, n, _ptr(T[n]))
+        for k in range(3):
+            s.origin[k] = self.origin[k]
         for n in ['total_mass', 'izz', 'spacing0', 'xcm', 'vcm', 'ang_mom',
                   'omega', 'force', 'torque', 'R', 'R_prev', 'xcm0', 'vcm0',
                   'ang_mom0', 'R0']:
@@ -347,6 +364,15 @@ class DeviceScene(object):
         self._graph = None
         self._canelas = None
         self.rebuild.fill_(1)
+        self.pos32_refresh()
+
+    def pos32_refresh(self):
+        """FP32 positions of every particle from x, y, z, h (after the host
+        wrote them; the step kernels keep them current themselves)."""
+        if self.n_total:
+            _lib.check(self.lib.rbx_pos32_refresh(
+                ctypes.byref(self._scene[0]), 0, self.n_total, self.stream),
+                'rbx_pos32_refresh')
 
     def points(self, index=None, n=None):
         p = RbxPoints()
@@ -363,7 +389,8 @@ class DeviceScene(object):
     def params(self, dt):
         return RbxParams(self.radius_scale, self.kr, self.kf,
                          self.fric_coeff, self.g[0], self.g[1], self.g[2],
-                         float(dt), self.reach, self.h_uniform, self.skin)
+                         float(dt), self.reach, self.h_uniform, self.skin,
+                         _lib.PARAM_EXACT if self.exact else 0, 0)
 
     def force_rebuild(self):
         """Neighbour lists must be rebuilt at the next force evaluation."""
@@ -411,6 +438,7 @@ class DeviceScene(object):
     def push_touched(self):
         """Upload whatever the host code touched since the last step."""
         rebuild = False
+        refresh32 = False
         for pa in self.arrays:
             touched = pa.__dict__['_host_touched']
             if not touched:
@@ -426,7 +454,11 @@ class DeviceScene(object):
                 t.copy_(torch.as_tensor(host, dtype=t.dtype))
                 if name in ('x', 'y', 'z', 'xcm', 'R'):
                     self.rebuild.fill_(1)      # positions changed under us
+                if name in ('x', 'y', 'z', 'h'):
+                    refresh32 = True
             touched.clear()
+        if refresh32 and not rebuild:
+            self.pos32_refresh()
         if rebuild:
             for pa in self.arrays:
                 for n in list(pa.__dict__['_device_newer']):
@@ -659,7 +691,9 @@ class DeviceScene(object):
     # ------------------------------------------------------------------
     # parity helpers
     # ------------------------------------------------------------------
-    def make_diag(self):
+    def make_diag(self, pair_cap=0):
+        """Per-slot diagnostics of a contact evaluation; pair_cap > 0 also
+        collects the neighbour pairs the contact kernel accepts."""
         nr = max(self.n_rigid, 1)
         K = _lib.RBX_MAX_KEYS
         dev = self.device
@@ -671,7 +705,38 @@ class DeviceScene(object):
         d = RbxDiag()
         for n, v in t.items():
             setattr(d, n, _ptr(v))
+        if pair_cap > 0:
+            t['pairs'] = torch.zeros(2 * pair_cap, dtype=torch.int32,
+                                     device=dev)
+            t['pair_count'] = torch.zeros(1, dtype=torch.int64, device=dev)
+            d.pairs, d.pair_count = _ptr(t['pairs']), _ptr(t['pair_count'])
+            d.pair_cap = int(pair_cap)
         return d, t
+
+    def contact_pairs(self, dt, pair_cap=None):
+        """The (destination, source) pairs one contact evaluation acts on --
+        every neighbour-list entry that passes the gate of
+        rigid_body_common.py:678-679 and the exact neighbour predicate with the
+        current positions -- as a sorted int array [npairs, 2] of GLOBAL
+        particle indices.  Uses the neighbour lists as they are (rebuilt only
+        if the rebuild flag is up) and leaves the history untouched."""
+        if pair_cap is None:
+            pair_cap = max(self.n_rigid, 1) * self.list_cap
+        d, t = self.make_diag(pair_cap)
+        d.key = None               # pairs only
+        p = self.params(dt)
+        self.push_touched()
+        self.cells_build()
+        _lib.check(self.lib.rbx_contact_mofidi(
+            ctypes.byref(self.scene), ctypes.byref(self._cells),
+            ctypes.byref(p), ctypes.byref(d), self.stream), 'pairs')
+        n = int(t['pair_count'].item())
+        if n > pair_cap:
+            raise _lib.RbxError('pair buffer too small: %d > %d' %
+                                (n, pair_cap))
+        out = t['pairs'][:2 * n].view(n, 2).cpu().numpy()
+        order = np.lexsort((out[:, 1], out[:, 0]))
+        return out[order]
 
     def history(self):
         """Current history as host arrays: key [ks,n], dlt/fn [3,ks,n]."""
@@ -680,6 +745,33 @@ class DeviceScene(object):
         return (h['key'].view(self.ks, nr).cpu().numpy(),
                 h['dlt'].view(3, self.ks, nr).cpu().numpy(),
                 h['fn'].view(3, self.ks, nr).cpu().numpy())
+
+    def set_history(self, name, key, dlt, fn):
+        """Load the contact history of rigid array ``name`` (restart from a
+        saved state): key [k, n] source dem_id per slot (-1 = unused, the used
+        ones first), dlt / fn [3, k, n] = delta_lt and fn of those slots
+        (rigid_body_common.py:1005-1012), k <= ks."""
+        pas = dict((a.name, a) for a in self.rigid)
+        o = self.p_off[name]
+        n = pas[name].get_number_of_particles()
+        key = np.asarray(key, dtype=np.int32)
+        k = key.shape[0]
+        if k > self.ks or key.shape[1] != n:
+            raise ValueError('history of %d slots x %d particles does not '
+                             'fit ks=%d, n=%d' % (k, key.shape[1], self.ks, n))
+        nr = max(self.n_rigid, 1)
+        h = self.H[self.parity]
+        hk = h['key'].view(self.ks, nr)
+        hd = h['dlt'].view(3, self.ks, nr)
+        hf = h['fn'].view(3, self.ks, nr)
+        hk[:, o:o + n] = -1
+        hd[:, :, o:o + n] = 0.
+        hf[:, :, o:o + n] = 0.
+        hk[:k, o:o + n] = self._t(key, torch.int32)
+        hd[:, :k, o:o + n] = self._t(np.asarray(dlt, dtype=np.float64),
+                                     torch.float64)
+        hf[:, :k, o:o + n] = self._t(np.asarray(fn, dtype=np.float64),
+                                     torch.float64)
 
     def pairs(self, dst_name, src_name):
         """NNPS neighbour pairs (i, j) of array dst among array src, as a
