@@ -1027,10 +1027,15 @@ k_slots(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
 // any list neighbour, L = list radius, all per component):
 //   stored coordinate      |d| <= u E         ->  XIJ:  ex = 2.1 u E
 //   r (FMA sum, MUFU.RSQ)  er = sqrt(3) ex + 4 u L;   q = r / h:  er / h
-//   W = T w(q):            |dW| <= T |w'(q)| er / h + (second order) + 9 u W,
-//                          |w'| <= D = 5 t3^4 + 30 t2^4 + 75 t1^4
+//   W = T w(q):            |dW| <= T max|w'| er / h + 9 u W  (mean value
+//                          theorem), and with dq = er / h, t_i clamped at 0:
+//                          |w'| <= 5 (t3+dq)^4 + 30 (t2+dq)^4 + 75 (t1+dq)^4
+//                               <= 1.34 (5 t3^4 + 30 t2^4 + 75 t1^4) + 1.5e5 dq^4
+//                          ((a+b)^4 <= 1.1^3 a^4 + 11^3 b^4) =: D; an entry
+//                          beyond the support adds only the dq^4 floor
 //   XIJ / r:               (ex + er) / r
-// so with the extra sums  SD = sum (T / h) (D + floor),  wA = sum tmp1:
+// so with the extra sums  SD = sum (T / h) D,  wA = sum tmp1:
+// (SD = sum (T / h) D)
 //   dw = er SD + cu w,   dA = sqrt3 ((ex + er) wA + dw),
 //   dB = sqrt3 (ex w + L dw),   cu = (list_cap + 16) u  (accumulation).
 // No contact is certain when
@@ -1081,7 +1086,8 @@ k_filter(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P
         h1 = 1.f / (0.5f * (me.w + h_uniform));
         T = vol * sigma * (DIM == 2 ? h1 * h1 : h1 * h1 * h1);
         Th = T * h1;
-        dfloor = 300.f * er * h1;
+        const float dq = er * h1;
+        dfloor = 1.5e5f * (dq * dq) * (dq * dq);
       }
 
       float ax = 0.f, ay = 0.f, az = 0.f, w1 = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
@@ -1099,22 +1105,21 @@ k_filter(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P
           asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(h1) : "f"(hij));
           T = vol * sigma * (DIM == 2 ? h1 * h1 : h1 * h1 * h1);
           Th = T * h1;
-          dfloor = 300.f * er * h1;
+          const float dq = er * h1;
+          dfloor = 1.5e5f * (dq * dq) * (dq * dq);
         }
         const float q = r * h1;
         const float t3 = fmaxf(3.f - q, 0.f), t2 = fmaxf(2.f - q, 0.f), t1 = fmaxf(1.f - q, 0.f);
         const float a3 = t3 * t3, a2 = t2 * t2, a1 = t1 * t1;
         const float b3 = a3 * a3, b2 = a2 * a2, b1 = a1 * a1;
         const float wv = fmaf(15.f, b1 * t1, fmaf(-6.f, b2 * t2, b3 * t3));
-        const float Dq = fmaf(75.f, b1, fmaf(30.f, b2, fmaf(5.f, b3, dfloor)));
+        const float Dq = fmaf(100.5f, b1, fmaf(40.2f, b2, fmaf(6.7f, b3, dfloor)));
         const float tmp2 = T * wv;
         const float tmp1 = tmp2 * rinv;
         ax = fmaf(dx, tmp1, ax); ay = fmaf(dy, tmp1, ay); az = fmaf(dz, tmp1, az);
         bx = fmaf(dx, tmp2, bx); by = fmaf(dy, tmp2, by); bz = fmaf(dz, tmp2, bz);
         w1 += tmp2;
         wA += tmp1;
-        // entries beyond the support add their floor only (D = 0 there, but
-        // the rounded q may sit on the other side of 3)
         SD = fmaf(Th, Dq, SD);
         if (t3 > 0.f) npairs++;
         if (qc < 0) {                              // last entry of a source body

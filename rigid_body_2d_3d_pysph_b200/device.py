@@ -739,12 +739,20 @@ class DeviceScene(object):
         return out[order]
 
     def history(self):
-        """Current history as host arrays: key [ks,n], dlt/fn [3,ks,n]."""
+        """Current history as host arrays: key [ks,n], dlt/fn [3,ks,n].  The
+        kernels end a particle's entries with one key of -1 and leave what
+        follows stale; here everything past the terminator reads as unused
+        (key -1, zeros)."""
         h = self.H[self.parity]
         nr = max(self.n_rigid, 1)
-        return (h['key'].view(self.ks, nr).cpu().numpy(),
-                h['dlt'].view(3, self.ks, nr).cpu().numpy(),
-                h['fn'].view(3, self.ks, nr).cpu().numpy())
+        key = h['key'].view(self.ks, nr).cpu().numpy().copy()
+        dlt = h['dlt'].view(3, self.ks, nr).cpu().numpy().copy()
+        fn = h['fn'].view(3, self.ks, nr).cpu().numpy().copy()
+        used = np.logical_and.accumulate(key >= 0, axis=0)
+        key[~used] = -1
+        dlt[:, ~used] = 0.
+        fn[:, ~used] = 0.
+        return key, dlt, fn
 
     def set_history(self, name, key, dlt, fn):
         """Load the contact history of rigid array ``name`` (restart from a

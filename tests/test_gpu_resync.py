@@ -61,8 +61,9 @@ def _dense_history_matches(what, sc, oarr, rigid):
     # cubes reach the floor near step 105
     ('benchmark_5_3d', (120, 80, 200)),
     ('stack_of_cylinders', (20, 180, 400)),
-    ('benchmark_3', (200, 300)),
-    ('benchmark_4', (200, 300)),
+    # first contact between steps 2000 and 3000
+    ('benchmark_3', (2600, 400, 600)),
+    ('benchmark_4', (2450, 100, 150)),   # in contact 2380..2760, then rebounds
     ('benchmark_5_2d', (200, 300)),
     ('benchmark_2', (1100, 200)),
 ])
