@@ -50,8 +50,6 @@ typedef enum {
 #define RBX_STATUS_GRID_COARSENED 8u /* cell size enlarged to fit cap_cells    */
 #define RBX_STATUS_LVC_OVERFLOW 16u  /* LVC tangential history `limit` hit     */
 #define RBX_STATUS_PAIR_OVERFLOW 32u /* RbxDiag.pairs buffer full              */
-#define RBX_STATUS_RUN_OVERFLOW 64u  /* run-major list storage full (cap_ent,
-                                        cap_blk) or > 255 runs on a particle */
 
 #define RBX_MAX_KEYS 8   /* slots per particle the optional RbxDiag arrays hold */
 
@@ -126,28 +124,19 @@ typedef struct {
   const int32_t *body_chunk;  /* [n_bodies + 1] chunk ranges per body    */
   /* Neighbour lists.  nbr_pos[list_cap][n_rigid] (column = particle): global
    * index of every gated source within reach + skin of the particle when the
-   * list was built, the sources of one body contiguous ("run"), bit 31 set on
-   * the first entry of a run; nbr_cnt[n_rigid] entries per particle (bit 30:
+   * list was built, the sources of one body contiguous, bit 31 set on the
+   * first entry of a body; nbr_cnt[n_rigid] entries per particle (bit 30:
    * a body may own more than one run of this list).  Built by
    * rbx_contact_neighbours when *rebuild != 0, reused otherwise.
-   *
-   * What the contact kernels read is the RUN-MAJOR copy made at the same
-   * time (k_runs), per window of 256 consecutive particles: the runs of the
-   * window sorted by descending length and cut into blocks of 32, a lane of
-   * a warp <-> one run.  Run reference r = 32 * block + lane:
-   *   run_desc[r]  = particle - window base (8 bits) | ordinal of the run in
-   *                  its particle's list << 8 (8 bits) | length << 16; -1 = no run
-   *   run_blk[2b]  = first entry of block b in run_ent, run_blk[2b+1] = its
-   *                  longest run; entry e of lane l: run_ent[first + 32 e + l]
-   *   win_blk[2w], win_blk[2w+1] = first block and number of blocks of window w
-   *   run_idx[run_first[p] + k] = reference of run k of particle p,
-   *   run_cnt[p]   = its number of runs (bit 30 as in nbr_cnt).
-   * counters[4] / [5] = blocks / entries handed out (cap_blk, cap_ent).
-   * The kernels apply the exact neighbour predicate to every entry with the
-   * current positions, so the pair set is independent of the skin.        */
+   * rbx_contact_slots reads the transposed copy made at the same time:
+   * work item t <-> particle nbr_order[t], the particles of every window of
+   * 256 ordered by descending list length (so that the lanes of a warp run
+   * lists of equal length); nbr_cnt_srt[t] entries in column t of
+   * nbr_srt[list_cap][n_rigid], bit 31 set on the LAST entry of a body.  It
+   * applies the exact neighbour predicate to every entry with the current
+   * positions, so the pair set is independent of the skin.               */
   int32_t *nbr_pos, *nbr_cnt;
-  int32_t *run_ent, *run_desc, *run_blk, *run_idx, *run_first, *run_cnt, *win_blk;
-  int64_t cap_ent, cap_blk;
+  int32_t *nbr_order, *nbr_cnt_srt, *nbr_srt;
   /* per body */
   const double *total_mass, *izz, *spacing0; /* [n_bodies]               */
   double *xcm, *vcm, *ang_mom, *omega;       /* [3 n_bodies]             */
@@ -184,7 +173,7 @@ typedef struct {
    * particles by rbx_contact_neighbours on a rebuild.  A first pass sums
    * every (particle, source body) slot in FP32 with a running error bound
    * and proves most of them out of contact; clist[2 n_rigid] receives
-   * {particle, bit mask of the runs that could not be excluded} and only
+   * {work item, bit mask of the runs that could not be excluded} and only
    * those are evaluated by the exact FP64 code.  counters[6] = entries.     */
   float *pos32;
   int32_t *clist;

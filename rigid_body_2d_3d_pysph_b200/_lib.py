@@ -20,7 +20,6 @@ STATUS_LIST_OVERFLOW = 4
 STATUS_GRID_COARSENED = 8
 STATUS_LVC_OVERFLOW = 16
 STATUS_PAIR_OVERFLOW = 32
-STATUS_RUN_OVERFLOW = 64
 PARAM_EXACT = 1
 
 POSE_POS, POSE_VEL, POSE_VEL_PREV, POSE_NORMALS = 1, 2, 4, 8
@@ -50,9 +49,8 @@ _SCENE_INTS = ['n_total', 'n_rigid', 'n_bodies', 'n_chunks', 'dim', 'ks',
 _SCENE_PTRS = ['x', 'y', 'z', 'u', 'v', 'w', 'h', 'm', 'rho', 'dem_id',
                'fx', 'fy', 'fz', 'dx0', 'dy0', 'dz0', 'body', 'is_boundary',
                'normal0', 'normal', 'chunk_start', 'chunk_body', 'body_chunk',
-               'nbr_pos', 'nbr_cnt', 'run_ent', 'run_desc', 'run_blk',
-               'run_idx', 'run_first', 'run_cnt', 'win_blk', 'cap_ent',
-               'cap_blk', 'total_mass', 'izz', 'spacing0', 'xcm', 'vcm',
+               'nbr_pos', 'nbr_cnt', 'nbr_order', 'nbr_cnt_srt',
+               'nbr_srt', 'total_mass', 'izz', 'spacing0', 'xcm', 'vcm',
                'ang_mom', 'omega', 'force', 'torque', 'R', 'R_prev', 'iinv_b',
                'iinv_g', 'xcm0', 'vcm0', 'ang_mom0', 'R0', 'eta', 'eta_row',
                'hist_key_in', 'hist_dlt_in', 'hist_fn_in', 'hist_key_out',

@@ -57,6 +57,7 @@ namespace {
 #endif
 constexpr int kWarps = RBX_CHUNK / 32;
 constexpr int kBatch = 4;        // staged candidates per thread per iteration
+constexpr int kLd = RBX_KLD;     // list entries in flight per thread in k_slots
 
 constexpr int kHash = RBX_CHUNK;                 // hash slots = group ids of a tile
 constexpr int kGIter = RBX_TILE / RBX_CHUNK;     // tile entries per thread
@@ -435,179 +436,129 @@ __global__ void k_list_commit(RbxScene S) {
 }
 
 __global__ void k_list_clear(RbxScene S, double skin) {
-  if (S.counters) {
-    S.counters[7] = 0ull;      // chunk dispenser of k_neighbours
-    S.counters[4] = 0ull;      // run blocks / entries handed out by k_runs
-    S.counters[5] = 0ull;
-  }
+  if (S.counters) S.counters[7] = 0ull;      // chunk dispenser of k_neighbours
   // skin == 0: no reuse, the flag stays up and every evaluation rebuilds
   if (S.rebuild && S.xcm_ref && skin > 0.) *S.rebuild = 0u;
 }
 
-// ---- lists as the contact kernels read them: run-major -----------------------
-// A "run" = the entries of one source body in one particle's list: the unit
-// the contact law works on (one (particle, source body) slot).  On a rebuild,
-// per window of kWin consecutive particles, the runs of the window are sorted
-// by descending length (counting sort) and cut into blocks of 32: lane l of a
-// warp <-> run 32 b + l, entry e of that run at run_ent[first_b + 32 e + l]
-// (a 128-byte row per entry and warp).  k_filter then does the FP32 sums of a
-// run in one thread and tests the run ONCE, all 32 lanes together, when the
-// block is through -- in particle-major lists the lanes of a warp reach the
-// ends of their runs at different entries and that test ran on 3 lanes of 32
-// at every other entry (40 % of the kernel's instructions).  The exact pass
-// (k_slots) finds the runs of a particle through run_idx.
-constexpr int kWin = 256;          // particles per window = threads per CTA
-constexpr int kRunBins = 2048;     // run lengths (list_cap < 2048)
-constexpr int kWinBlkCap = 512;    // run blocks per window (16384 runs)
-constexpr int kStageCap = 16384;   // entries staged in (dynamic) shared memory per window
+// ---- lists as the pair kernel reads them ------------------------------------
+// On a rebuild, per window of kSortW consecutive particles: a stable counting
+// sort of the particles by descending list length (work item t <-> particle
+// nbr_order[t]) and a transposition of the lists into that order (column t of
+// nbr_srt), through shared memory so that both the read and the write
+// coalesce.  The run marker moves from the first to the LAST entry of a
+// source body on the way.  k_slots then
+//   * runs warps whose 32 lists have (nearly) the same length -- in particle
+//     order the lengths range from 0 (interior) to 60+ (corners) inside one
+//     warp and 60 % of the lanes idle,
+//   * accumulates the sums of one source body in registers and parks the
+//     slot when the marked entry has been added: no key search, no
+//     shared-memory read-modify-write per pair.
+#ifndef RBX_SORT_W
+#define RBX_SORT_W 256
+#endif
+#ifndef RBX_SORT_ROWS
+#define RBX_SORT_ROWS 32
+#endif
+constexpr int kSortW = RBX_SORT_W;       // particles per window = threads per CTA
+constexpr int kSortBins = 256;
+constexpr int kSortRows = RBX_SORT_ROWS; // list rows staged in shared memory at a time
+static_assert(kSortW >= kSortBins && kSortW % 32 == 0 && kSortW <= 1024, "kSortW");
 
-__global__ void __launch_bounds__(kWin, 2)
-k_runs(RbxScene S) {
+__global__ void __launch_bounds__(kSortW, 1024 / kSortW)
+k_list_sort(RbxScene S) {
   if (S.rebuild && *S.rebuild == 0u) return;      // lists still valid
-  __shared__ int start[kRunBins];     // runs longer than the bin's length
-  __shared__ int fill[kRunBins];
-  __shared__ int boff[kWinBlkCap + 1];            // first entry of a block (window-local)
-  __shared__ int wsum[kWin / 32];
-  __shared__ int s_base[2];
-  extern __shared__ int stage[];      // kStageCap entries
+  __shared__ int stage[kSortRows + 1][kSortW];    // [row][particle of the window]
+  __shared__ int cnt[kSortW / 32][kSortBins];
+  __shared__ int start[kSortBins];
+  __shared__ int perm[kSortW];                    // sorted slot -> particle of the window
+  __shared__ int lens[kSortW];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int w = blockIdx.x;
-  const int base = w * kWin;
+  const int base = blockIdx.x * kSortW;
   const int p = base + tid;
   const bool valid = p < S.n_rigid;
-  const int cnt_raw = valid ? S.nbr_cnt[p] : 0;
-  const int len = cnt_raw & (kSplitBit - 1);
+  const int len_raw = valid ? S.nbr_cnt[p] : 0;
+  const int len = len_raw & (kSplitBit - 1);
   const size_t n = (size_t)S.n_rigid;
-  const int *col = S.nbr_pos + (valid ? p : 0);
 
-  for (int i = tid; i < kRunBins; i += kWin) { start[i] = 0; fill[i] = 0; }
+  // ---- 1. stable counting sort of the window by descending list length ------
+  // bin 0 = threads past the end (sorted last), bin len + 1 otherwise
+  const int key = valid ? (len < kSortBins - 2 ? len : kSortBins - 2) + 1 : 0;
+  for (int i = tid; i < (kSortW / 32) * kSortBins; i += kSortW) (&cnt[0][0])[i] = 0;
   __syncthreads();
-  // ---- 1. histogram of the run lengths, runs per particle ---------------------
-  int nruns = 0;
-  {
-    int cur = 0;
-    const int *c = col;
-    for (int e = 0; e < len; e++, c += n) {
-      if (*c < 0 && e > 0) { atomicAdd(&start[cur < kRunBins ? cur : kRunBins - 1], 1); nruns++; cur = 0; }
-      cur++;
+  const unsigned grp = __match_any_sync(0xffffffffu, key);
+  const int within = __popc(grp & ((1u << lane) - 1u));
+  if (within == 0) cnt[wid][key] = __popc(grp);
+  __syncthreads();
+  if (tid < kSortBins) {                // per bin: exclusive prefix over warps
+    int run = 0;
+#pragma unroll
+    for (int w2 = 0; w2 < kSortW / 32; w2++) {
+      const int c = cnt[w2][tid];
+      cnt[w2][tid] = run;
+      run += c;
     }
-    if (len > 0) { atomicAdd(&start[cur < kRunBins ? cur : kRunBins - 1], 1); nruns++; }
+    start[tid] = run;
   }
   __syncthreads();
-  // ---- 2. ranks: descending exclusive scan over the bins ----------------------
-  auto block_excl_scan = [&](int v, int &total) -> int {   // exclusive prefix over threads
-    int inc = v;
+  if (wid == 0) {                       // descending exclusive scan over bins
+    constexpr int per = kSortBins / 32;
+    int tot[per], sum = 0;
+#pragma unroll
+    for (int j = 0; j < per; j++) { tot[j] = start[kSortBins - 1 - (per * lane + j)]; sum += tot[j]; }
+    int inc = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const int t2 = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += t2;
+      const int v = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += v;
     }
-    __syncthreads();                   // previous users of wsum are done
-    if (lane == 31) wsum[wid] = inc;
+    int run = inc - sum;
+#pragma unroll
+    for (int j = 0; j < per; j++) { start[kSortBins - 1 - (per * lane + j)] = run; run += tot[j]; }
+  }
+  __syncthreads();
+  const int slot = start[key] + cnt[wid][key] + within;   // in [0, kSortW)
+  perm[slot] = tid;
+  lens[tid] = len_raw;
+  if (valid) S.nbr_order[base + slot] = p;
+  int maxlen = len;                     // window maximum (strip loop bound)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
+  __syncthreads();                      // perm, lens complete; cnt is free
+  if (lane == 0) cnt[0][wid] = maxlen;
+  __syncthreads();
+  maxlen = 0;
+#pragma unroll
+  for (int w2 = 0; w2 < kSortW / 32; w2++) maxlen = max(maxlen, cnt[0][w2]);
+
+  // ---- 2. transpose, kSortRows list rows at a time (+ 1 row of lookahead) ----
+  const int src = perm[tid];            // the particle whose list this thread writes out
+  const int len_out_raw = lens[src];
+  const int len_out = len_out_raw & (kSplitBit - 1);
+  const int t = base + tid;             // ... into column t
+  const int *rp = S.nbr_pos + p;
+  for (int o0 = 0; o0 < maxlen; o0 += kSortRows) {
+    const int r_in = min(len - o0, kSortRows + 1);
+    {
+      const int *c = rp + (size_t)o0 * n;
+      for (int r = 0; r < r_in; r++, c += n) stage[r][tid] = *c;
+    }
     __syncthreads();
-    int off = 0, tot = 0;
-#pragma unroll
-    for (int w2 = 0; w2 < kWin / 32; w2++) { if (w2 < wid) off += wsum[w2]; tot += wsum[w2]; }
-    total = tot;
-    return off + inc - v;
-  };
-  int R;                                // runs of the window
-  {
-    constexpr int per = kRunBins / kWin;
-    int c[per], sum = 0;
-#pragma unroll
-    for (int j = 0; j < per; j++) { c[j] = start[kRunBins - 1 - (per * tid + j)]; sum += c[j]; }
-    int run = block_excl_scan(sum, R);
-#pragma unroll
-    for (int j = 0; j < per; j++) { start[kRunBins - 1 - (per * tid + j)] = run; run += c[j]; }
-  }
-  int tot_runs;
-  const int my_first = block_excl_scan(nruns, tot_runs);   // CSR offset of this particle's runs
-  const int nblk = (R + 31) >> 5;
-  // longest run of block b = length of the run of rank 32 b = the smallest
-  // length l with start[l] <= 32 b (start[] does not increase with l)
-  const int nb_eff = nblk < kWinBlkCap ? nblk : kWinBlkCap;
-  int E = 0;                            // entries of the window incl. padding
-  for (int b0 = 0; b0 < nb_eff; b0 += kWin) {
-    const int b = b0 + tid;
-    int L = 0;
-    if (b < nb_eff) {
-      int lo = 1, hi = kRunBins - 1;
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (start[mid] <= 32 * b) hi = mid; else lo = mid + 1;
-      }
-      L = lo;
-    }
-    int tot;
-    const int ex = block_excl_scan(32 * L, tot);
-    if (b < nb_eff) boff[b] = E + ex;
-    E += tot;
-  }
-  if (tid == 0) boff[nb_eff] = E;
-  __syncthreads();
-  // ---- 3. storage for the window ---------------------------------------------
-  if (tid == 0) {
-    bool ok = nblk <= kWinBlkCap;
-    long long rb0 = 0, e0 = 0;
-    if (ok) {
-      rb0 = (long long)atomicAdd(&S.counters[4], (unsigned long long)nblk);
-      e0 = (long long)atomicAdd(&S.counters[5], (unsigned long long)E);
-      ok = rb0 + nblk <= S.cap_blk && e0 + E <= S.cap_ent;
-    }
-    if (!ok && S.status) atomicOr(S.status, RBX_STATUS_RUN_OVERFLOW);
-    s_base[0] = ok ? (int)rb0 : -1;
-    s_base[1] = (int)e0;
-    S.win_blk[2 * w] = ok ? (int)rb0 : 0;
-    S.win_blk[2 * w + 1] = ok ? nblk : 0;
-  }
-  __syncthreads();
-  const int rb0 = s_base[0], e0 = s_base[1];
-  if (rb0 < 0) {                        // no room: the window has no runs at all
-    if (valid) { S.run_first[p] = 0; S.run_cnt[p] = 0; }
-    return;
-  }
-  for (int b = tid; b < nblk; b += kWin) {
-    S.run_blk[2 * (rb0 + b)] = e0 + boff[b];
-    S.run_blk[2 * (rb0 + b) + 1] = (boff[b + 1] - boff[b]) >> 5;
-  }
-  for (int r = tid; r < 32 * nblk; r += kWin) S.run_desc[32 * rb0 + r] = -1;   // empty lanes
-  __syncthreads();
-  const bool staged = E <= kStageCap;
-  // ---- 4. place every run -----------------------------------------------------
-  if (valid) {
-    S.run_first[p] = 32 * rb0 + my_first;
-    S.run_cnt[p] = (nruns < 256 ? nruns : 255) | (cnt_raw & kSplitBit);
-    if (nruns > 255 && S.status) atomicOr(S.status, RBX_STATUS_RUN_OVERFLOW);
-    int k = 0, s0 = 0;
-    const int *c = col;
-    for (int e = 0; e <= len; e++, c += n) {
-      if (e == len || (e > 0 && *c < 0)) {          // run [s0, e) is complete
-        const int l = e - s0;
-        if (l > 0 && k < 255) {
-          const int bin = l < kRunBins ? l : kRunBins - 1;
-          const int rank = start[bin] + atomicAdd(&fill[bin], 1);
-          const int blk = rank >> 5, ln = rank & 31;
-          const int ref = 32 * (rb0 + blk) + ln;
-          S.run_desc[ref] = tid | (k << 8) | (l << 16);
-          S.run_idx[32 * rb0 + my_first + k] = ref;
-          const int *src = col + (size_t)s0 * n;
-          int dst = boff[blk] + ln;
-          for (int j = 0; j < l; j++, src += n, dst += 32) {
-            const int q = *src & 0x7fffffff;
-            if (staged) stage[dst] = q; else S.run_ent[e0 + dst] = q;
-          }
-          k++;
-        }
-        s0 = e;
-        if (e == len) break;
+    if (t < S.n_rigid) {
+      const int r1 = min(len_out - o0, kSortRows);
+      int *out = S.nbr_srt + (size_t)o0 * n + t;
+      int v = r1 > 0 ? stage[0][src] : 0;
+      for (int r = 0; r < r1; r++, out += n) {
+        // last entry of a source body <=> the next entry starts one
+        const bool more = o0 + r + 1 < len_out;
+        const int nv = more ? stage[r + 1][src] : -1;
+        *out = (int)(((unsigned)v & 0x7fffffffu) | (nv < 0 ? kRunBit : 0u));
+        v = nv;
       }
     }
-  }
-  if (staged) {
     __syncthreads();
-    for (int i = tid; i < E; i += kWin) S.run_ent[e0 + i] = stage[i];
   }
+  if (t < S.n_rigid) S.nbr_cnt_srt[t] = len_out_raw;
 }
 
 constexpr int kSlotsCta = RBX_SLOTS_CTA;   // threads per CTA of k_slots
@@ -810,9 +761,9 @@ park_overflow(double (*ovf)[kFields], int nk, double ax, double ay, double az, d
 }
 
 // One work item = one particle and the runs of its list that have to be
-// evaluated exactly.  COMPACT = false: every particle, every run (the
+// evaluated exactly.  clist == nullptr: every particle, every run (the
 // reference semantics in one pass; diagnostics, pair dump).  Otherwise item i
-// of the compact list written by k_filter: {particle, bit mask of the runs
+// of the compact list written by k_filter: {work item t, bit mask of the runs
 // that the FP32 pass could not exclude (bit 31 = run 31 and every later one)}.
 template <int DIM, bool UNIFORM_H, bool COMPACT>
 __global__ void __launch_bounds__(kSlotsCta, RBX_SLOTS_MINB)
@@ -822,38 +773,46 @@ k_slots(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
   // (closest source, some in-range source of the body) as two ints.
   __shared__ double acc[kAcc][kFields][kSlotsCta];
 
-  // The per-body force/torque sum is done by k_reduce.
+  // work item t <-> particle nbr_order[t] (k_list_sort): full warps of equal
+  // list length.  The per-body force/torque sum is done by k_reduce.
   const int tid = threadIdx.x, lane = tid & 31;
   const size_t n_rigid = (size_t)S.n_rigid;
   unsigned nactive = 0, npairs = 0;
 
   // Persistent CTAs, every one resident from the start, striding over the
-  // blocks of kSlotsCta work items.  A finished warp takes its next block at
-  // once instead of waiting for a CTA launch.
+  // blocks of kSlotsCta work items (the grid size is odd: a stride that is a
+  // multiple of the 8 warps of a sort window would give a CTA the same length
+  // class every time).  A finished warp takes its next block at once instead
+  // of waiting for a CTA launch.
   const int nwork = COMPACT ? (int)S.counters[6] : S.n_rigid;
   const int nitems = (nwork + kSlotsCta - 1) / kSlotsCta;
-  // particle of the work item after this one: loaded a whole item ahead, so
-  // that its data can be pulled into L2 while this item finishes
-  int p_next = -1, cnt_next = 0;
+  // particle and list length of the work item after this one: loaded a whole
+  // item ahead, so that its particle data and first list rows can be pulled
+  // into L2 while this item finishes (a warp otherwise starts every item with
+  // three dependent DRAM round trips and nothing to overlap them with)
+  int p_next = -1, cnt_next = 0, t_next = 0;
   unsigned mask_next = 0xffffffffu;
   auto fetch_item = [&](int i) {
     p_next = -1;
     if (i < nwork) {
-      p_next = i;
-      if (COMPACT) { p_next = S.clist[2 * i]; mask_next = (unsigned)S.clist[2 * i + 1]; }
-      cnt_next = S.run_cnt[p_next];
+      t_next = i;
+      if (COMPACT) { t_next = S.clist[2 * i]; mask_next = (unsigned)S.clist[2 * i + 1]; }
+      p_next = S.nbr_order[t_next];
+      cnt_next = S.nbr_cnt_srt[t_next];
     }
   };
   fetch_item(blockIdx.x * kSlotsCta + tid);
   for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+  const int t = t_next;
   const bool valid = p_next >= 0;
   const int p = p_next;
   const int cnt_raw = cnt_next;
   const unsigned run_mask = mask_next;
   if (item + gridDim.x < nitems) fetch_item((item + gridDim.x) * kSlotsCta + tid);
   else p_next = -1;
+  const int tn = t_next;
   if (valid) {
-    const int nruns = cnt_raw & (kSplitBit - 1);
+    const int nlist = cnt_raw & (kSplitBit - 1);
     // partial slots of a split body and the slots of a diagnostics run are
     // all parked; otherwise only those that pass the contact prefilter
     const bool park_all = (cnt_raw & kSplitBit) != 0 || D.key != nullptr;
@@ -873,6 +832,7 @@ k_slots(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
     int qmin = -1;           // its global index
     bool touched = false;    // some entry passed the neighbour predicate
     int nk = 0;              // slots parked in shared memory
+    int run = 0;             // ordinal of the source-body run being read
     SlotOut so;
     so.cfx = so.cfy = so.cfz = 0.;
     so.nout = 0; so.ki = 0; so.st = 0u; so.nactive = 0u;
@@ -898,6 +858,25 @@ k_slots(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
     // the predicate only gates the closest-point search), which doubles the
     // instruction-level parallelism of what is otherwise one long dependent
     // FP64 chain per entry; the sums are then added in list order.
+    // Software pipeline: entries e + 2 + j (j < kLd) are loaded (coalesced
+    // stream from HBM), the positions of sources e + 2, e + 3 are being
+    // gathered (L1/L2) while entries e, e + 1 are processed.
+    static_assert(kLd >= 2 && kLd % 2 == 0, "kLd");
+    int ql[kLd];
+    const int *cl = S.nbr_srt + t;
+#pragma unroll
+    for (int j = 0; j < kLd; j++) ql[j] = (2 + j < nlist) ? cl[(size_t)(2 + j) * n_rigid] : 0;
+    int qc0 = nlist > 0 ? cl[0] : 0;
+    int qc1 = nlist > 1 ? cl[n_rigid] : 0;
+    cl += (size_t)(2 + kLd) * n_rigid;
+    double c0x, c0y, c0z, c0h = 0., c1x, c1y, c1z, c1h = 0.;
+    {
+      const int qi = qc0 & 0x7fffffff, qj = qc1 & 0x7fffffff;
+      c0x = S.x[qi]; c0y = S.y[qi]; c0z = S.z[qi];
+      if (!UNIFORM_H) c0h = S.h[qi];
+      c1x = S.x[qj]; c1y = S.y[qj]; c1z = S.z[qj];
+      if (!UNIFORM_H) c1h = S.h[qj];
+    }
     const double hmax2_u = fmax(hi2, hj2_u);
     auto pair_math = [&](double sx, double sy, double sz, double sh, double &x0, double &x1,
                          double &x2, double &r2, double &tmp1, double &tmp2, bool &in) {
@@ -959,46 +938,50 @@ k_slots(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
         r2thr = rmin0 * rmin0; qmin = -1; touched = false;
       }
     };
-    // The runs of this particle (run_idx), those the FP32 pass has excluded
-    // stepped over (an excluded slot adds exactly nothing:
-    // rigid_body_common.py:1014-1027).  Entry e of a run sits at
-    // run_ent[first + 32 e]; add_pair takes bit 31 on the last entry of the
-    // run as the signal to close the slot.
-    const int *ridx = S.run_idx + S.run_first[p];
-    for (int k = 0; k < nruns; k++) {
-      if (COMPACT && ((run_mask >> (k < 31 ? k : 31)) & 1u) == 0u) continue;
-      const int ref = ridx[k];
-      const int len = S.run_desc[ref] >> 16;
-      const int *ce = S.run_ent + S.run_blk[2 * (ref >> 5)] + (ref & 31);
-      int qn0 = ce[0], qn1 = len > 1 ? ce[32] : 0;
-      double c0x = S.x[qn0], c0y = S.y[qn0], c0z = S.z[qn0];
-      double c1x = S.x[qn1], c1y = S.y[qn1], c1z = S.z[qn1];
-      double c0h = 0., c1h = 0.;
-      if (!UNIFORM_H) { c0h = S.h[qn0]; c1h = S.h[qn1]; }
-      for (int e0 = 0; e0 < len; e0 += 2) {
-        const int qc0 = qn0 | (e0 + 1 == len ? (int)kRunBit : 0);
-        const int qc1 = qn1 | (e0 + 2 == len ? (int)kRunBit : 0);
-        // next pair of entries: indices, then positions
-        qn0 = e0 + 2 < len ? ce[32 * (e0 + 2)] : 0;
-        qn1 = e0 + 3 < len ? ce[32 * (e0 + 3)] : 0;
-        const double g0x = S.x[qn0], g0y = S.y[qn0], g0z = S.z[qn0];
-        const double g1x = S.x[qn1], g1y = S.y[qn1], g1z = S.z[qn1];
-        double g0h = 0., g1h = 0.;
-        if (!UNIFORM_H) { g0h = S.h[qn0]; g1h = S.h[qn1]; }
+    // COMPACT: is the run with this ordinal one of those to evaluate?
+    auto selected = [&](int r) -> bool {
+      return !COMPACT || ((run_mask >> (r < 31 ? r : 31)) & 1u) != 0u;
+    };
+#pragma unroll 2
+    for (int e0 = 0; e0 < nlist; e0 += 2) {
+      // stage G for entries e0 + 2, e0 + 3; stage L for e0 + 2 + kLd, + 3 + kLd
+      const int qn0 = ql[0], qn1 = ql[1];
+      const int i0 = qn0 & 0x7fffffff, i1 = qn1 & 0x7fffffff;
+      const double g0x = S.x[i0], g0y = S.y[i0], g0z = S.z[i0];
+      const double g1x = S.x[i1], g1y = S.y[i1], g1z = S.z[i1];
+      double g0h = 0., g1h = 0.;
+      if (!UNIFORM_H) { g0h = S.h[i0]; g1h = S.h[i1]; }
+#pragma unroll
+      for (int j = 0; j + 2 < kLd; j++) ql[j] = ql[j + 2];
+      ql[kLd - 2] = (e0 + 2 + kLd < nlist) ? cl[0] : 0;
+      ql[kLd - 1] = (e0 + 3 + kLd < nlist) ? cl[n_rigid] : 0;
+      cl += 2 * n_rigid;
+      // runs the FP32 pass has excluded are only stepped over (an excluded
+      // slot adds exactly nothing: rigid_body_common.py:1014-1027)
+      const bool s0 = selected(run);
+      const int run1 = run + (qc0 < 0 ? 1 : 0);
+      const bool s1 = e0 + 1 < nlist && selected(run1);
+      if (s0 || s1) {
         double a0, a1, a2, ar, at1, at2, b0, b1, b2, br, bt1, bt2;
         bool ain, bin;
         pair_math(c0x, c0y, c0z, c0h, a0, a1, a2, ar, at1, at2, ain);
         pair_math(c1x, c1y, c1z, c1h, b0, b1, b2, br, bt1, bt2, bin);
-        add_pair(qc0, a0, a1, a2, ar, at1, at2, ain);
-        if (e0 + 1 < len) add_pair(qc1, b0, b1, b2, br, bt1, bt2, bin);
-        c0x = g0x; c0y = g0y; c0z = g0z; c0h = g0h;
-        c1x = g1x; c1y = g1y; c1z = g1z; c1h = g1h;
+        if (s0) add_pair(qc0, a0, a1, a2, ar, at1, at2, ain);
+        if (s1) add_pair(qc1, b0, b1, b2, br, bt1, bt2, bin);
       }
+      run = run1 + ((e0 + 1 < nlist && qc1 < 0) ? 1 : 0);
+      qc0 = qn0; c0x = g0x; c0y = g0y; c0z = g0z; c0h = g0h;
+      qc1 = qn1; c1x = g1x; c1y = g1y; c1z = g1z; c1h = g1h;
     }
     if (p_next >= 0) {
       rbx_prefetch_l2(S.x + p_next); rbx_prefetch_l2(S.y + p_next); rbx_prefetch_l2(S.z + p_next);
       rbx_prefetch_l2(S.h + p_next); rbx_prefetch_l2(S.m + p_next); rbx_prefetch_l2(S.rho + p_next);
-      rbx_prefetch_l2(S.body + p_next); rbx_prefetch_l2(S.run_first + p_next);
+      rbx_prefetch_l2(S.body + p_next);
+      const int *ln = S.nbr_srt + tn;
+      const int nl = cnt_next & (kSplitBit - 1);
+#pragma unroll
+      for (int k = 0; k < 2 + kLd; k++)
+        if (k < nl) rbx_prefetch_l2(ln + (size_t)k * n_rigid);
     }
     if (nk > 0) finalize_slots(&S, &P, &D, acc, ovf, nk, p, tid, (cnt_raw & kSplitBit) != 0, &so);
     nactive += so.nactive;
@@ -1060,20 +1043,17 @@ k_slots(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
 // (|A| <= w, |B| <= L w), tested on squares; NaN (coincident points) fails the
 // test and is kept.  Runs past ordinal 30 share mask bit 31.
 #ifndef RBX_FILTER_MINB
-#define RBX_FILTER_MINB 4
+#define RBX_FILTER_MINB 32
 #endif
 
-// One CTA per window of kWin particles; a warp takes the run blocks of the
-// window in turn, lane <-> run (see k_runs).
 template <int DIM, bool UNIFORM_H>
-__global__ void __launch_bounds__(kWin, RBX_FILTER_MINB)
+__global__ void __launch_bounds__(32, RBX_FILTER_MINB)
 k_filter(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
          float h_uniform) {
-  __shared__ float4 s_me[kWin];       // x, y, z (relative to origin), h
-  __shared__ float4 s_c[kWin];        // vol * sigma, ex, spacing0^2, all-runs flag
-  __shared__ unsigned s_mask[kWin];   // runs that could not be excluded
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int lane = threadIdx.x;
+  const size_t n_rigid = (size_t)S.n_rigid;
   const float4 *__restrict__ pos = reinterpret_cast<const float4 *>(S.pos32);
+  const int nitems = (S.n_rigid + 31) / 32;
   unsigned npairs = 0;
   constexpr float kU = 5.9604645e-8f;            // 2^-24
   constexpr float kSqrt3 = 1.7320509f;
@@ -1081,111 +1061,114 @@ k_filter(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P
   const float cu = (float)(S.list_cap + 16) * kU;
   const float sigma = DIM == 2 ? (float)(0.31830988618379067154 * 7.0 / 478.0)
                                : (float)(0.31830988618379067154 / 120.0);
-  const int nwin = (S.n_rigid + kWin - 1) / kWin;
 
-  for (int w = blockIdx.x; w < nwin; w += gridDim.x) {
-    const int p = w * kWin + tid;
-    const bool valid = p < S.n_rigid;
-    __syncthreads();                   // the previous window is done with s_*
+  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int t = item * 32 + lane;
+    const bool valid = t < S.n_rigid;
+    unsigned mask = 0u;
     if (valid) {
+      const int p = S.nbr_order[t];
+      const int cnt_raw = S.nbr_cnt_srt[t];
+      const int nlist = cnt_raw & (kSplitBit - 1);
+      const bool all = (cnt_raw & kSplitBit) != 0;   // split bodies: partial sums
       const float4 me = pos[p];
       const float s0 = (float)S.spacing0[S.body[p]];
       const float vol = (float)(S.m[p] / S.rho[p]);
+      // error coefficients of this particle
       const float E = fmaxf(fmaxf(fabsf(me.x), fabsf(me.y)), fabsf(me.z)) + Lr;
-      s_me[tid] = me;
-      s_c[tid] = make_float4(vol * sigma, 2.1f * kU * E, s0 * s0 * 1.0001f,
-                             (S.run_cnt[p] & kSplitBit) ? 1.f : 0.f);
-    }
-    s_mask[tid] = 0u;
-    __syncthreads();
-    const int rb0 = S.win_blk[2 * w], nblk = S.win_blk[2 * w + 1];
-    for (int b = wid; b < nblk; b += kWin / 32) {
-      const int d = S.run_desc[32 * (rb0 + b) + lane];
-      const int2 bl = reinterpret_cast<const int2 *>(S.run_blk)[rb0 + b];
-      const int L = bl.y;
-      const int len = d < 0 ? 0 : (d >> 16);
-      const int pl = d & (kWin - 1);
-      const float4 me = s_me[pl];
-      const float4 cc = s_c[pl];
-      // error coefficients of this particle (see above)
-      const float ex = cc.y;
+      const float ex = 2.1f * kU * E;
       const float er = kSqrt3 * ex + 4.f * kU * Lr;
       const float eu = ex + er;
+      const float s0sq = s0 * s0 * 1.0001f;
+      // uniform h: constants of the kernel
       float h1 = 0.f, Th = 0.f, T = 0.f, dfloor = 0.f;
       if (UNIFORM_H) {
         h1 = 1.f / (0.5f * (me.w + h_uniform));
-        T = cc.x * (DIM == 2 ? h1 * h1 : h1 * h1 * h1);
+        T = vol * sigma * (DIM == 2 ? h1 * h1 : h1 * h1 * h1);
         Th = T * h1;
         const float dq = er * h1;
         dfloor = 1.5e5f * (dq * dq) * (dq * dq);
       }
+
       float ax = 0.f, ay = 0.f, az = 0.f, w1 = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
       float wA = 0.f, SD = 0.f;
-      // list entries two rows ahead, positions one row ahead
-      const int *ce = S.run_ent + bl.x + lane;
-      int q1 = 1 < len ? ce[32] : 0;
-      float4 sp = pos[0 < len ? ce[0] : 0];
-      for (int e = 0; e < L; e++) {
-        const float4 sn = pos[q1];
-        q1 = e + 2 < len ? ce[32 * (e + 2)] : 0;
-        if (e < len) {
-          const float dx = me.x - sp.x, dy = me.y - sp.y, dz = me.z - sp.z;
-          const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-          float rinv;
-          asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(r2));
-          const float r = r2 * rinv;
-          if (!UNIFORM_H) {
-            const float hij = 0.5f * (me.w + sp.w);
-            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(h1) : "f"(hij));
-            T = cc.x * (DIM == 2 ? h1 * h1 : h1 * h1 * h1);
-            Th = T * h1;
-            const float dq = er * h1;
-            dfloor = 1.5e5f * (dq * dq) * (dq * dq);
-          }
-          const float q = r * h1;
-          const float t3 = fmaxf(3.f - q, 0.f), t2 = fmaxf(2.f - q, 0.f), t1 = fmaxf(1.f - q, 0.f);
-          const float a3 = t3 * t3, a2 = t2 * t2, a1 = t1 * t1;
-          const float b3 = a3 * a3, b2 = a2 * a2, b1 = a1 * a1;
-          const float wv = fmaf(15.f, b1 * t1, fmaf(-6.f, b2 * t2, b3 * t3));
-          const float Dq = fmaf(100.5f, b1, fmaf(40.2f, b2, fmaf(6.7f, b3, dfloor)));
-          const float tmp2 = T * wv;
-          const float tmp1 = tmp2 * rinv;
-          ax = fmaf(dx, tmp1, ax); ay = fmaf(dy, tmp1, ay); az = fmaf(dz, tmp1, az);
-          bx = fmaf(dx, tmp2, bx); by = fmaf(dy, tmp2, by); bz = fmaf(dz, tmp2, bz);
-          w1 += tmp2;
-          wA += tmp1;
-          SD = fmaf(Th, Dq, SD);
-          if (t3 > 0.f) npairs++;
+      int run = 0;
+
+      auto entry = [&](int qc, const float4 sp) {
+        const float dx = me.x - sp.x, dy = me.y - sp.y, dz = me.z - sp.z;
+        const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        float rinv;
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(r2));
+        const float r = r2 * rinv;
+        if (!UNIFORM_H) {
+          float hij = 0.5f * (me.w + sp.w);
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(h1) : "f"(hij));
+          T = vol * sigma * (DIM == 2 ? h1 * h1 : h1 * h1 * h1);
+          Th = T * h1;
+          const float dq = er * h1;
+          dfloor = 1.5e5f * (dq * dq) * (dq * dq);
         }
-        sp = sn;
+        const float q = r * h1;
+        const float t3 = fmaxf(3.f - q, 0.f), t2 = fmaxf(2.f - q, 0.f), t1 = fmaxf(1.f - q, 0.f);
+        const float a3 = t3 * t3, a2 = t2 * t2, a1 = t1 * t1;
+        const float b3 = a3 * a3, b2 = a2 * a2, b1 = a1 * a1;
+        const float wv = fmaf(15.f, b1 * t1, fmaf(-6.f, b2 * t2, b3 * t3));
+        const float Dq = fmaf(100.5f, b1, fmaf(40.2f, b2, fmaf(6.7f, b3, dfloor)));
+        const float tmp2 = T * wv;
+        const float tmp1 = tmp2 * rinv;
+        ax = fmaf(dx, tmp1, ax); ay = fmaf(dy, tmp1, ay); az = fmaf(dz, tmp1, az);
+        bx = fmaf(dx, tmp2, bx); by = fmaf(dy, tmp2, by); bz = fmaf(dz, tmp2, bz);
+        w1 += tmp2;
+        wA += tmp1;
+        SD = fmaf(Th, Dq, SD);
+        if (t3 > 0.f) npairs++;
+        if (qc < 0) {                              // last entry of a source body
+          const float dw = fmaf(er, SD, cu * w1);
+          const float dA = kSqrt3 * fmaf(eu, wA, dw);
+          const float dB = kSqrt3 * fmaf(ex, w1, Lr * dw);
+          const float ab = fmaf(az, bz, fmaf(ay, by, ax * bx));
+          const float aa = fmaf(az, az, fmaf(ay, ay, ax * ax));
+          const float eab = 1.01f * fmaf(dA, dB, w1 * fmaf(Lr, dA, dB));
+          const float lhs = ab - eab;
+          const float aahi = fmaf(dA, fmaf(2.f, w1, dA), aa);
+          const float wh = w1 + dw;
+          const float rhs = s0sq * (wh * wh) * aahi;
+          // w <= 1e-12: the slot has no normal, dist = 0, overlap == spacing0
+          const bool drop = (wh < 0.99e-12f) || (lhs > 0.f && lhs * lhs > rhs);
+          if (!drop || all) mask |= 1u << (run < 31 ? run : 31);
+          run++;
+          ax = ay = az = w1 = bx = by = bz = 0.f;
+          wA = SD = 0.f;
+        }
+      };
+
+      // software pipeline: the list entries of the next pair of entries are
+      // in flight while the positions of this one are gathered
+      const int *cl = S.nbr_srt + t;
+      int qa = nlist > 0 ? cl[0] : 0;
+      int qb = nlist > 1 ? cl[n_rigid] : 0;
+      int la = nlist > 2 ? cl[2 * n_rigid] : 0;
+      int lb = nlist > 3 ? cl[3 * n_rigid] : 0;
+      cl += 4 * n_rigid;
+      float4 sa = pos[qa & 0x7fffffff], sb = pos[qb & 0x7fffffff];
+      for (int e0 = 0; e0 < nlist; e0 += 2) {
+        const float4 ga = pos[la & 0x7fffffff], gb = pos[lb & 0x7fffffff];
+        const int na = (e0 + 4 < nlist) ? cl[0] : 0;
+        const int nb = (e0 + 5 < nlist) ? cl[n_rigid] : 0;
+        cl += 2 * n_rigid;
+        entry(qa, sa);
+        if (e0 + 1 < nlist) entry(qb, sb);
+        qa = la; qb = lb; sa = ga; sb = gb; la = na; lb = nb;
       }
-      // the run is complete in every lane: one test, no divergence
-      const float dw = fmaf(er, SD, cu * w1);
-      const float dA = kSqrt3 * fmaf(eu, wA, dw);
-      const float dB = kSqrt3 * fmaf(ex, w1, Lr * dw);
-      const float ab = fmaf(az, bz, fmaf(ay, by, ax * bx));
-      const float aa = fmaf(az, az, fmaf(ay, ay, ax * ax));
-      const float eab = 1.01f * fmaf(dA, dB, w1 * fmaf(Lr, dA, dB));
-      const float lhs = ab - eab;
-      const float aahi = fmaf(dA, fmaf(2.f, w1, dA), aa);
-      const float wh = w1 + dw;
-      const float rhs = cc.z * (wh * wh) * aahi;
-      // w <= 1e-12: the slot has no normal, dist = 0, overlap == spacing0
-      const bool drop = (wh < 0.99e-12f) || (lhs > 0.f && lhs * lhs > rhs);
-      if (d >= 0 && (!drop || cc.w != 0.f)) {
-        const int k = (d >> 8) & 255;
-        atomicOr(&s_mask[pl], 1u << (k < 31 ? k : 31));
+      if (mask == 0u) {
+        // nothing can be in contact: BodyForce alone (:122-125), no history
+        const double md = S.m[p];
+        S.fx[p] = md * P.gx; S.fy[p] = md * P.gy; S.fz[p] = md * P.gz;
+        S.hist_key_out[p] = -1;
       }
     }
-    __syncthreads();
-    const unsigned mask = valid ? s_mask[tid] : 0u;
-    if (valid && mask == 0u) {
-      // nothing can be in contact: BodyForce alone (:122-125), no history
-      const double md = S.m[p];
-      S.fx[p] = md * P.gx; S.fy[p] = md * P.gy; S.fz[p] = md * P.gz;
-      S.hist_key_out[p] = -1;
-    }
-    // the rest goes to the exact pass: {particle, run mask}
+    // the rest goes to the exact pass: {work item, run mask}, appended in
+    // lane order (which block of the list a warp gets does not matter)
     const unsigned bal = __ballot_sync(0xffffffffu, mask != 0u);
     if (bal) {
       int base = 0;
@@ -1193,7 +1176,7 @@ k_filter(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P
       base = __shfl_sync(0xffffffffu, base, 0);
       if (mask != 0u) {
         const int k = base + __popc(bal & ((1u << lane) - 1u));
-        S.clist[2 * k] = p;
+        S.clist[2 * k] = t;
         S.clist[2 * k + 1] = (int)mask;
       }
     }
@@ -1222,9 +1205,7 @@ static int check_contact_args(const RbxScene *scene, const RbxCells *cells, cons
   if (scene->ks < 1 || (scene->dim != 2 && scene->dim != 3)) return RBX_ERR_INVALID;
   if (!(params->reach > 0.) || scene->list_cap < 1) return RBX_ERR_INVALID;
   if (!scene->nbr_pos || !scene->nbr_cnt || !scene->counters) return RBX_ERR_INVALID;
-  if (!scene->run_ent || !scene->run_desc || !scene->run_blk || !scene->run_idx ||
-      !scene->run_first || !scene->run_cnt || !scene->win_blk) return RBX_ERR_INVALID;
-  if (scene->list_cap >= kRunBins || scene->cap_ent < 1 || scene->cap_blk < 1) return RBX_ERR_INVALID;
+  if (!scene->nbr_srt || !scene->nbr_order || !scene->nbr_cnt_srt) return RBX_ERR_INVALID;
   return RBX_OK;
 }
 
@@ -1248,9 +1229,7 @@ extern "C" int rbx_contact_neighbours(const RbxScene *scene, const RbxCells *cel
     const int nbp = rbx_blocks(n, 256), capp = rbx_sm_count() * 8;
     k_pos32<<<nbp < capp ? nbp : capp, 256, 0, st>>>(*scene, scene->n_rigid, n, 1);
   }
-  cudaFuncSetAttribute(k_runs, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       kStageCap * (int)sizeof(int));
-  k_runs<<<rbx_blocks(scene->n_rigid, kWin), kWin, kStageCap * sizeof(int), st>>>(*scene);
+  k_list_sort<<<rbx_blocks(scene->n_rigid, kSortW), kSortW, 0, st>>>(*scene);
   if (scene->rebuild)
     k_list_commit<<<rbx_blocks(scene->n_bodies, 256), 256, 0, st>>>(*scene);
   k_list_clear<<<1, 1, 0, st>>>(*scene, params->skin);
@@ -1283,23 +1262,23 @@ extern "C" int rbx_contact_slots(const RbxScene *scene, const RbxCells *cells,
   // two-precision evaluation unless the caller asks for the one-pass FP64
   // evaluation, wants per-slot diagnostics, or has no FP32 positions
   const bool fast = scene->pos32 && scene->clist && !(params->flags & RBX_PARAM_EXACT) &&
-                    !d.key && !d.pairs;
+                    !d.key && !d.pairs && scene->list_cap < (1 << 20);
   // all CTAs resident at once (RBX_SLOTS_MINB per SM), odd count
   int ng = rbx_blocks(scene->n_rigid, kSlotsCta);
   const int resident = sms * RBX_SLOTS_MINB - 1;
   if (ng > resident) ng = resident;
   if (fast) {
     cudaMemsetAsync(&scene->counters[6], 0, sizeof(unsigned long long), st);
-    int nf = rbx_blocks(scene->n_rigid, kWin);
-    const int resf = sms * RBX_FILTER_MINB * 8;
+    int nf = rbx_blocks(scene->n_rigid, 32);
+    const int resf = sms * RBX_FILTER_MINB - 1;
     if (nf > resf) nf = resf;
     const float hu = (float)params->h_uniform;
     if (scene->dim == 3) {
-      if (uni) k_filter<3, true><<<nf, kWin, 0, st>>>(*scene, *params, hu);
-      else k_filter<3, false><<<nf, kWin, 0, st>>>(*scene, *params, 0.f);
+      if (uni) k_filter<3, true><<<nf, 32, 0, st>>>(*scene, *params, hu);
+      else k_filter<3, false><<<nf, 32, 0, st>>>(*scene, *params, 0.f);
     } else {
-      if (uni) k_filter<2, true><<<nf, kWin, 0, st>>>(*scene, *params, hu);
-      else k_filter<2, false><<<nf, kWin, 0, st>>>(*scene, *params, 0.f);
+      if (uni) k_filter<2, true><<<nf, 32, 0, st>>>(*scene, *params, hu);
+      else k_filter<2, false><<<nf, 32, 0, st>>>(*scene, *params, 0.f);
     }
     if (scene->dim == 3) {
       if (uni) k_slots<3, true, true><<<ng, kSlotsCta, 0, st>>>(*scene, *params, d, params->h_uniform);

@@ -55,7 +55,7 @@ class DeviceScene(object):
                  kr=1e5, kf=1e3, fric_coeff=0.5, gx=0., gy=0., gz=0.,
                  planar=False, ks=8, radius_scale=3.0, eta_uniform=None,
                  cap_cells=None, list_cap=96, skin_factor=0.05, device=None,
-                 exact=False, run_cap=16):
+                 exact=False):
         if not torch.cuda.is_available():
             raise _lib.RbxError('DeviceScene needs a CUDA device; the '
                                 'rigid-body path has no CPU fallback')
@@ -83,8 +83,6 @@ class DeviceScene(object):
         # in one pass (RBX_PARAM_EXACT); default: FP32 first pass with an
         # error bound, FP64 for what it cannot exclude -- identical results
         self.exact = bool(exact)
-        self.run_cap = int(run_cap)   # runs (source bodies) per particle,
-        #                               on average, the run-major lists hold
         self._cap_cells_req = cap_cells
         self.parity = 0          # history ping-pong
         self.steps_done = 0
@@ -216,24 +214,12 @@ class DeviceScene(object):
         self.T['nbr_pos'] = torch.empty(self.list_cap * nr_, dtype=i32,
                                         device=dev)
         self.T['nbr_cnt'] = torch.zeros(nr_, dtype=i32, device=dev)
-        # the same lists run-major, as the contact kernels read them (k_runs,
-        # on every rebuild): cap_ent bounds entries + padding (at most one
-        # row of a block per window on top of the lists themselves), cap_blk
-        # the blocks of 32 runs (run_cap runs per particle on average)
-        nwin = (nr_ + 255) // 256
-        self.cap_ent = self.list_cap * (nr_ + 32 * nwin)
-        self.cap_blk = nwin + (nr_ * min(self.list_cap, self.run_cap) + 31) \
-            // 32
-        self.T['run_ent'] = torch.empty(self.cap_ent, dtype=i32, device=dev)
-        self.T['run_desc'] = torch.empty(32 * self.cap_blk, dtype=i32,
-                                         device=dev)
-        self.T['run_idx'] = torch.empty(32 * self.cap_blk, dtype=i32,
+        # the same lists as the pair kernel reads them (length-ordered work
+        # items, entries grouped by source body), made on every rebuild
+        self.T['nbr_srt'] = torch.empty(self.list_cap * nr_, dtype=i32,
                                         device=dev)
-        self.T['run_blk'] = torch.zeros(2 * self.cap_blk, dtype=i32,
-                                        device=dev)
-        self.T['run_first'] = torch.zeros(nr_, dtype=i32, device=dev)
-        self.T['run_cnt'] = torch.zeros(nr_, dtype=i32, device=dev)
-        self.T['win_blk'] = torch.zeros(2 * nwin, dtype=i32, device=dev)
+        self.T['nbr_order'] = torch.arange(nr_, dtype=i32, device=dev)
+        self.T['nbr_cnt_srt'] = torch.zeros(nr_, dtype=i32, device=dev)
         # two-precision contact evaluation: FP32 positions relative to the
         # centre of the scene and the compact list of the exact pass
         self.T['pos32'] = torch.zeros(4 * max(self.n_total, 1),
@@ -342,11 +328,9 @@ class DeviceScene(object):
             s.normal = _ptr(P['normal'])
         s.list_cap = self.list_cap
         for n in ['chunk_start', 'chunk_body', 'body_chunk', 'nbr_pos',
-                  'nbr_cnt', 'run_ent', 'run_desc', 'run_blk', 'run_idx',
-                  'run_first', 'run_cnt', 'win_blk',
+                  'nbr_cnt', 'nbr_srt', 'nbr_order', 'nbr_cnt_srt',
                   'eta', 'eta_row', 'pos32', 'clist']:
             setattr(s, n, _ptr(T[n]))
-        s.cap_ent, s.cap_blk = self.cap_ent, self.cap_blk
         for k in range(3):
             s.origin[k] = self.origin[k]
         for n in ['total_mass', 'izz', 'spacing0', 'xcm', 'vcm', 'ang_mom',
@@ -688,10 +672,6 @@ class DeviceScene(object):
             msgs.append('per-particle neighbour list overflow (list_cap=%d; '
                         'pass a larger list_cap or a smaller skin_factor)'
                         % self.list_cap)
-        if st & _lib.STATUS_RUN_OVERFLOW:
-            msgs.append('run-major neighbour lists full (run_cap=%d runs per '
-                        'particle on average, 255 at most on one particle)' %
-                        self.run_cap)
         if msgs and raise_on_error:
             raise _lib.RbxError('device status 0x%x: %s' %
                                 (st, '; '.join(msgs)))

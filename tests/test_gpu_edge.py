@@ -215,13 +215,12 @@ def test_device_boundary_identification_equals_host():
 
 
 def test_neighbour_list_structures():
-    """The data structures between the contact kernels, on configs 3 and 4:
-    nbr_pos lists grouped by source body with the first entry of a body
-    marked; the run-major copy (k_runs): every run of every particle reachable
-    through run_idx with the right particle, ordinal and length, its entries
-    those of the list, the runs of a window sorted by descending length in
-    blocks of 32, run_blk = longest run of the block; and the lists a
-    superset of the exact neighbour sets restricted to gated sources."""
+    """The data structures between the three contact kernels, on configs 3
+    and 4: nbr_pos lists grouped by source body with the first entry of a
+    body marked; nbr_order a permutation of every 256-particle window in
+    descending list length; nbr_srt the same lists, transposed into that
+    order, with the LAST entry of a body marked; and the lists a superset of
+    the exact neighbour sets restricted to gated sources."""
     from rigid_body_2d_3d_pysph_b200.device import DeviceScene
     from tests.util import load_config
     for name in ('benchmark_5_3d', 'stack_of_cylinders'):
@@ -236,60 +235,37 @@ def test_neighbour_list_structures():
         n, cap = sc.n_rigid, sc.list_cap
         raw = sc.T['nbr_pos'].view(cap, n).cpu().numpy()
         cnt = sc.T['nbr_cnt'].cpu().numpy()
-        ent = sc.T['run_ent'].cpu().numpy()
-        desc = sc.T['run_desc'].cpu().numpy()
-        blk = sc.T['run_blk'].cpu().numpy().reshape(-1, 2)
-        ridx = sc.T['run_idx'].cpu().numpy()
-        rfirst = sc.T['run_first'].cpu().numpy()
-        rcnt = sc.T['run_cnt'].cpu().numpy()
-        wblk = sc.T['win_blk'].cpu().numpy().reshape(-1, 2)
+        srt = sc.T['nbr_srt'].view(cap, n).cpu().numpy()
+        order = sc.T['nbr_order'].cpu().numpy()
+        cnt_s = sc.T['nbr_cnt_srt'].cpu().numpy()
         dem = sc.P['dem_id'].cpu().numpy()
         x, y, z, h = (sc.P[k].cpu().numpy() for k in 'xyzh')
         src = np.zeros(sc.n_total, bool)
         src[sc.T['src_index'].cpu().numpy()] = True
         lens = cnt & 0x3fffffff
         assert lens.max() > 0, name
-        # windows: blocks of 32 runs in descending length
-        total_runs = 0
-        for w in range(wblk.shape[0]):
-            rb0, nblk = wblk[w]
-            d = desc[32 * rb0:32 * (rb0 + nblk)]
-            used = d >= 0
-            ln = np.where(used, d >> 16, 0)
-            assert np.all(np.diff(ln) <= 0), (name, w)      # empty lanes last
-            for b in range(nblk):
-                assert blk[rb0 + b, 1] == ln[32 * b:32 * b + 32].max()
-            pl = d[used] & 255
-            assert (pl < min(256, n - 256 * w)).all()
-            total_runs += int(used.sum())
-        assert total_runs == int((rcnt & 0x3fffffff).sum())
+        # windows of 256: a permutation, longest lists first
+        for w0 in range(0, n, 256):
+            o = order[w0:w0 + 256]
+            assert np.array_equal(np.sort(o), np.arange(w0, min(w0 + 256, n)))
+            assert np.all(np.diff(lens[o]) <= 0), (name, w0)
+        assert np.array_equal(cnt_s, cnt[order])
         reach2 = (sc.reach + sc.skin)**2
-        for p in range(n):
-            ln = lens[p]
+        for t in range(n):
+            p, ln = order[t], lens[order[t]]
             a = raw[:ln, p].astype(np.int64)
-            qa = a & 0x7fffffff
+            b = srt[:ln, t].astype(np.int64)
+            qa, qb = a & 0x7fffffff, b & 0x7fffffff
+            assert np.array_equal(qa, qb), (name, p)
             assert len(set(qa.tolist())) == ln            # no duplicates
             assert src[qa].all() and (dem[qa] != dem[p]).all()
             d = dem[qa]
             first = np.r_[True, d[1:] != d[:-1]] if ln else np.zeros(0, bool)
+            last = np.r_[d[1:] != d[:-1], True] if ln else np.zeros(0, bool)
             assert np.array_equal(a < 0, first), (name, p)  # bit 31 (int32 sign)
+            assert np.array_equal(b < 0, last), (name, p)
             if not (cnt[p] >> 30) & 1:                     # one run per body
                 assert len(set(d[first].tolist())) == int(first.sum())
-            # run-major copy: the same entries, run by run
-            nr = rcnt[p] & 0x3fffffff
-            assert nr == int(first.sum()), (name, p)
-            assert (rcnt[p] >> 30) == (cnt[p] >> 30)
-            got = []
-            for k in range(nr):
-                ref = ridx[rfirst[p] + k]
-                dd = desc[ref]
-                assert dd >= 0 and (dd & 255) == p % 256 and \
-                    ((dd >> 8) & 255) == k, (name, p, k)
-                l = dd >> 16
-                base = blk[ref >> 5, 0] + (ref & 31)
-                got.append(ent[base + 32 * np.arange(l)])
-            got = np.concatenate(got) if got else np.zeros(0, np.int64)
-            assert np.array_equal(got, qa), (name, p)
             # superset of the gated sources within the reach (lists were
             # built from the positions of this very step)
             r2 = (x - x[p])**2 + (y - y[p])**2 + (z - z[p])**2
