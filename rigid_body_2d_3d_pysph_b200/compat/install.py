@@ -37,7 +37,6 @@ def install(force=False):
                    wall_normal)
     from .. import (boundary_particles, rigid_body_2d, rigid_body_3d,
                     rigid_body_common)
-    from .. import geometry as rb_geometry
     import builtins
 
     def declare(type, num=1):
@@ -96,7 +95,9 @@ def install(force=False):
     sys.modules['rigid_body_3d'] = rigid_body_3d
     sys.modules['rigid_body_2d'] = rigid_body_2d
     sys.modules['boundary_particles'] = boundary_particles
-    sys.modules['geometry'] = rb_geometry
+    # (`geometry`, the scripts' scene helper, is the script's own sibling: it
+    # only needs pysph.tools.geometry, registered above; run.py puts the
+    # script's directory on sys.path)
     try:
         importlib.import_module('matplotlib')
     except ImportError:

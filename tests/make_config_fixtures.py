@@ -53,6 +53,7 @@ DROP_CONST = set()
 
 def main():
     install()
+    sys.path.insert(0, REF)     # the scripts' own sibling geometry.py
     out_dir = os.path.join(ROOT, 'tests', 'golden')
     for name, (script, cls, argv) in CONFIGS.items():
         ns = runpy.run_path(REF + script, run_name='fixture')
