@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RBX_VERSION 300 /* 0.3.0 */
+#define RBX_VERSION 301 /* 0.3.1 */
 
 typedef enum {
   RBX_OK = 0,
@@ -166,6 +166,11 @@ typedef struct {
   uint32_t *rebuild;
   double *xcm_ref, *R_ref;    /* [3 n_bodies], [9 n_bodies] at last build */
   const double *rmax;         /* [n_bodies] max |body-frame position|     */
+  /* [n_bodies] first body (global index) of the particle array the body
+   * belongs to, or NULL = one array.  RK2RigidBody3DStep.py_initialize saves
+   * the angular momentum of the FIRST body of every array only
+   * (rigid_body_3d.py:415, quirk Q7).                                      */
+  const int32_t *body_first;
   /* Two-precision contact evaluation (optional: both NULL -> every slot is
    * evaluated in FP64).  pos32[n_total] = {x - origin[0], y - origin[1],
    * z - origin[2], h} as floats, kept current by rbx_pose_particles (rigid

@@ -199,6 +199,33 @@ def case_rk2_3d():
                 notes='RK2RigidBody3DStep under EPEC sequencing, nb=1')
 
 
+def case_rk2_3d_nb2():
+    """Two bodies in ONE array under the RK2 stepper: py_initialize saves the
+    angular momentum of body 0 only (rigid_body_3d.py:415, quirk Q7), so body
+    1 integrates from whatever ang_mom0 held at setup."""
+    dx = 0.05
+    xb, yb, zb = get_3d_block(dx, 2 * dx, 2 * dx, 2 * dx)
+    n = len(xb)
+    x = np.concatenate([xb, xb + 0.3 * dx])
+    y = np.concatenate([yb, yb + 3 * dx - 0.03 * dx])
+    z = np.concatenate([zb, zb - 0.2 * dx])
+    bid = np.concatenate([np.zeros(n, int), np.ones(n, int)])
+    body = _body('body', x, y, z, dx, dx, 2000., 3, bid, bid.copy(), 3)
+    xt, yt, zt = get_3d_block(dx, 6 * dx, dx, 6 * dx)
+    yt += min(y) - max(yt) - 0.97 * dx
+    tank = _wall('tank', xt, yt, zt, dx, dx, 2000., 3, 2)
+    s = rigid_body_3d.RigidBody3DScheme(['body'], ['tank'], dim=3, gy=-9.81)
+    s.kf = 1e3
+    _finish(s, [body], [tank])
+    tank.contact_force_is_boundary[:] = 1.
+    s.set_linear_velocity(body, np.array([0.1, 0., 0.05, -0.2, -0.1, 0.]))
+    s.set_angular_velocity(body, np.array([0.3, -0.2, 0.4, 0.5, 1.0, -0.7]))
+    return Case('rk2_3d_nb2', s, [body, tank], 1e-4, 'rk2',
+                save_steps=(1, 2, 5, 10, 20), nsteps=20,
+                notes='RK2RigidBody3DStep under EPEC sequencing, nb=2 in one '
+                      'array (quirk Q7: ang_mom0 of body 0 only)')
+
+
 def run_case(case):
     kernel = QuinticSpline(dim=case.scheme.dim)
     eqs = case.scheme.get_equations()
@@ -425,6 +452,7 @@ CASES = {
     'collide2d': case_collide2d,
     'cubes3d': case_cubes3d,
     'rk2_3d': case_rk2_3d,
+    'rk2_3d_nb2': case_rk2_3d_nb2,
 }
 
 if __name__ == '__main__':

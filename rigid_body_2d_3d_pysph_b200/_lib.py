@@ -55,7 +55,7 @@ _SCENE_PTRS = ['x', 'y', 'z', 'u', 'v', 'w', 'h', 'm', 'rho', 'dem_id',
                'iinv_g', 'xcm0', 'vcm0', 'ang_mom0', 'R0', 'eta', 'eta_row',
                'hist_key_in', 'hist_dlt_in', 'hist_fn_in', 'hist_key_out',
                'hist_dlt_out', 'hist_fn_out', 'status', 'counters', 'rebuild',
-               'xcm_ref', 'R_ref', 'rmax', 'pos32', 'clist']
+               'xcm_ref', 'R_ref', 'rmax', 'body_first', 'pos32', 'clist']
 
 
 class RbxScene(ctypes.Structure):

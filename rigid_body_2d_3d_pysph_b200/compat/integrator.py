@@ -23,7 +23,9 @@ class Integrator(object):
     def __init__(self, **kw):
         self.steppers = kw
         self.scene = None
-        self.fix_q7 = True
+        # reference behaviour (quirk Q7, rigid_body_3d.py:415) unless the
+        # stepper asks for the repaired save: one default on every entry point
+        self.fix_q7 = False
 
     def set_scene(self, scene):
         self.scene = scene

@@ -15,6 +15,8 @@ coherence protocol: reading ``pa.<prop>`` pulls the property from the GPU if
 the device copy is newer and marks it "host touched", so that it is pushed
 back before the next step.  No arithmetic of the hot path runs here.
 """
+import zlib
+
 import numpy as np
 
 _TYPE_MAP = {
@@ -50,6 +52,7 @@ class ParticleArray(object):
         d['_device'] = None
         d['_device_newer'] = set()
         d['_host_touched'] = set()
+        d['_host_read'] = {}
         self._n = 0
         if props:
             self._initialize(**props)
@@ -151,6 +154,40 @@ class ParticleArray(object):
         self.__dict__['_host_touched'].add(name)
         self.__dict__['_device_newer'].discard(name)
 
+    def touch(self, *names):
+        """Declare properties / constants modified in place by host code."""
+        for name in names:
+            self._touch(name)
+
+    def _note_read(self, name, arr):
+        """A read hands out the live array, which the caller may modify in
+        place (``pa.x[:] += 0.25``) without this object ever hearing of it.
+        While a device scene is bound, remember a checksum of what was handed
+        out (once per name between two steps); ``modified_since_read`` then
+        tells a read from a write, so that a callback that only LOOKS at
+        ``pa.m`` or ``pa.x`` does not force an upload, a static-table rebuild
+        or a neighbour-list rebuild at the next step."""
+        d = self.__dict__
+        if d['_device'] is None:
+            d['_host_touched'].add(name)
+            return
+        if name in d['_host_touched'] or name in d['_host_read']:
+            return
+        d['_host_read'][name] = zlib.crc32(memoryview(arr).cast('B'))
+
+    def modified_since_read(self):
+        """Names handed out since the last call whose content has changed."""
+        d = self.__dict__
+        out = set()
+        for name, crc in d['_host_read'].items():
+            arr = d['properties'].get(name)
+            if arr is None:
+                arr = d['constants'].get(name)
+            if arr is None or zlib.crc32(memoryview(arr).cast('B')) != crc:
+                out.add(name)
+        d['_host_read'].clear()
+        return out
+
     def _pull(self, name):
         d = self.__dict__
         if name in d['_device_newer'] and d['_device'] is not None:
@@ -162,12 +199,12 @@ class ParticleArray(object):
         props = d.get('properties')
         if props is not None and name in props:
             self._pull(name)
-            d['_host_touched'].add(name)
+            self._note_read(name, props[name])
             return props[name]
         consts = d.get('constants')
         if consts is not None and name in consts:
             self._pull(name)
-            d['_host_touched'].add(name)
+            self._note_read(name, consts[name])
             return consts[name]
         raise AttributeError("ParticleArray '%s' has no property or constant "
                              "'%s'" % (d.get('name'), name))

@@ -38,6 +38,9 @@ class Solver(object):
         self.list_cap = kwargs.pop('list_cap', 96)
         self.skin_factor = kwargs.pop('skin_factor', 0.05)
         self.use_graph = kwargs.pop('use_graph', True)
+        # one damping coefficient for every (body, body) pair instead of the
+        # reference's dense nb x tnb `eta` table (large scenes)
+        self.eta_uniform = kwargs.pop('eta_uniform', None)
         self.extra = kwargs
 
     # -- configuration hooks used by Application ---------------------------
@@ -76,6 +79,18 @@ class Solver(object):
         plan = plan_from_equations(equations, self.integrator)
         radius_scale = getattr(self.kernel, 'radius_scale', 3.0)
         self.plan = plan
+        if plan.kind != 'dem':
+            # The contact passes weight with WIJ (rigid_body_common.py:664,
+            # 793) and the device path evaluates the quintic spline only;
+            # any other kernel would silently run as a truncated quintic.
+            from .kernels import QuinticSpline
+            if self.kernel is not None and not (
+                    isinstance(self.kernel, QuinticSpline) and
+                    radius_scale == 3.0):
+                raise NotImplementedError(
+                    'the rigid-body contact path evaluates QuinticSpline '
+                    '(radius_scale 3) on the device; kernel %s is not '
+                    'mapped' % type(self.kernel).__name__)
         if plan.kind == 'dem':
             from ..dem import DemDeviceScene
             self.scene = DemDeviceScene(
@@ -88,7 +103,7 @@ class Solver(object):
             kf=plan.kf, fric_coeff=plan.fric_coeff, gx=plan.gx, gy=plan.gy,
             gz=plan.gz, planar=plan.planar, ks=self.ks,
             list_cap=self.list_cap, skin_factor=self.skin_factor,
-            radius_scale=radius_scale)
+            radius_scale=radius_scale, eta_uniform=self.eta_uniform)
         self.integrator.set_scene(self.scene)
         self.plan = plan
 

@@ -172,7 +172,9 @@ __global__ void k_rk2(RbxScene S, int stage, double dt, int fix_q7, double skin)
     for (int j = 0; j < 3; j++) {
       S.xcm0[i3 + j] = S.xcm[i3 + j];
       S.vcm0[i3 + j] = S.vcm[i3 + j];
-      if (fix_q7 || b == 0) S.ang_mom0[i3 + j] = S.ang_mom[i3 + j];
+      // :415 writes ang_mom0[j], j < 3: the first body of the array (Q7)
+      if (fix_q7 || (S.body_first ? S.body_first[b] == b : b == 0))
+        S.ang_mom0[i3 + j] = S.ang_mom[i3 + j];
     }
 #pragma unroll
     for (int k = 0; k < 9; k++) S.R0[i9 + k] = S.R[i9 + k];

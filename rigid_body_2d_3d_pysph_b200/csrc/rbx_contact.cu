@@ -86,6 +86,7 @@ k_neighbours(RbxScene S, RbxCells C, RbxParams P, double reach) {
   __shared__ int row_s[RBX_CHUNK], row_off[RBX_CHUNK + 1];
   __shared__ int wscan[kWarps];
   __shared__ int range[6];
+  __shared__ int s_shared_group;   // a tile held more source bodies than hash slots
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
@@ -98,8 +99,10 @@ k_neighbours(RbxScene S, RbxCells C, RbxParams P, double reach) {
   __shared__ int s_chunk;
   for (;;) {
   __syncthreads();              // shared memory of the previous chunk is free
-  if (tid == 0)
+  if (tid == 0) {
     s_chunk = S.counters ? (int)atomicAdd(&S.counters[7], 1ull) : -1;
+    s_shared_group = 0;
+  }
   __syncthreads();
   const int chunk = s_chunk;
   if (chunk < 0 || chunk >= S.n_chunks) break;
@@ -199,11 +202,19 @@ k_neighbours(RbxScene S, RbxCells C, RbxParams P, double reach) {
         if (j < tile_cnt) {
           const int d = r_dem[j];
           unsigned h = ((unsigned)d * 2654435761u) >> 25;
+          bool placed = false;
           for (int probe = 0; probe < kHash; probe++) {
             const int old = atomicCAS(&h_key[h], kEmptyKey, d);
-            if (old == kEmptyKey || old == d) break;
+            if (old == kEmptyKey || old == d) { placed = true; break; }
             h = (h + 1u) & (kHash - 1);
           }
+          // More than kHash source bodies in one tile (bodies of 1-4
+          // particles): this body shares the group of another one and the
+          // two come out as interleaved runs.  Every run is still one body
+          // (the run marks come from t_dem), so flagging the chunk as split
+          // makes k_filter keep and k_slots park every partial run, and
+          // finalize_slots adds them up by dem_id.
+          if (!placed) s_shared_group = 1;
           gk[k] = (int)h;
         }
         const unsigned grp = __match_any_sync(0xffffffffu, gk[k]);
@@ -408,7 +419,7 @@ k_neighbours(RbxScene S, RbxCells C, RbxParams P, double reach) {
   if (valid) {
     // bit 30: the chunk took more than one tile, a source body may own
     // several runs of the list
-    S.nbr_cnt[p] = nlist | (ntiles > 1 ? kSplitBit : 0);
+    S.nbr_cnt[p] = nlist | ((ntiles > 1 || s_shared_group) ? kSplitBit : 0);
     if (list_overflow && S.status) atomicOr(S.status, RBX_STATUS_LIST_OVERFLOW);
   }
   // counters: candidate distance tests, list entries written
@@ -690,7 +701,10 @@ finalize_slots(const RbxScene *Sp, const RbxParams *Pp, const RbxDiag *Dp,
       ovl_out = overlap;
       const double tmp = P.kr * overlap;
       double eta = 0.;
-      if (S.eta_mode == 1) eta = S.eta[S.eta_row[body] + key];       // :925
+      if (S.eta_mode == 1) {                                          // :925
+        const long long row = S.eta_row[body];   // < 0: array without a table
+        if (row >= 0) eta = S.eta[row + key];
+      }
       else if (S.eta_mode == 2) eta = S.eta[0];
       eta = eta * sqrt(md / 2. * P.kr);                               // :926
       const double fnx = (tmp - eta * vn) * nx;

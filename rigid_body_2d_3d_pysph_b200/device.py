@@ -91,6 +91,7 @@ class DeviceScene(object):
         for pa in self.arrays:
             pa.__dict__['_device'] = self
             pa.__dict__['_host_touched'].clear()
+            pa.__dict__['_host_read'].clear()
             pa.__dict__['_device_newer'].clear()
 
     # ------------------------------------------------------------------
@@ -195,6 +196,11 @@ class DeviceScene(object):
         if self.n_rigid:
             rmax.scatter_reduce_(0, self.P['body'].long(), r0, 'amax')
         self.B['rmax'] = rmax
+        # first body of the array a body belongs to (quirk Q7 of the RK2 step)
+        bf = [np.full(int(pa.constants['nb'][0]), self.b_off[pa.name])
+              for pa in self.rigid]
+        self.B['body_first'] = self._t(np.concatenate(bf) if bf
+                                       else np.zeros(0), i32)
         self.rebuild = torch.ones(1, dtype=i32, device=dev)
         # ---- chunks ----------------------------------------------------
         counts = np.bincount(body, minlength=self.n_bodies) \
@@ -242,8 +248,12 @@ class DeviceScene(object):
             for pa in self.rigid:
                 nb = int(pa.constants['nb'][0])
                 tnb = int(pa.constants['total_no_bodies'][0])
-                e = np.asarray(pa.constants.get('eta', np.zeros(nb * tnb)),
-                               dtype=np.float64)
+                # no 'eta' constant = no damping (eta_mode 0): nothing is
+                # materialised (nb * tnb doubles is 80 GB at 100 000 bodies)
+                if 'eta' not in pa.constants:
+                    rows.append(np.full(nb, -1, dtype=np.int64))
+                    continue
+                e = np.asarray(pa.constants['eta'], dtype=np.float64)
                 etas.append(e)
                 rows.append(eo + np.arange(nb, dtype=np.int64) * tnb)
                 eo += e.size
@@ -344,6 +354,7 @@ class DeviceScene(object):
         s.rebuild = _ptr(self.rebuild)
         s.xcm_ref, s.R_ref = _ptr(B['xcm_ref']), _ptr(B['R_ref'])
         s.rmax = _ptr(B['rmax'])
+        s.body_first = _ptr(B['body_first'])
         self._scene = [None, None]
         for par in (0, 1):
             c = RbxScene.from_buffer_copy(s)
@@ -441,6 +452,8 @@ class DeviceScene(object):
         refresh32 = False
         for pa in self.arrays:
             touched = pa.__dict__['_host_touched']
+            # reads hand out live arrays: what changed under a read counts
+            touched |= pa.modified_since_read()
             if not touched:
                 continue
             if touched & set(_STATIC):
@@ -465,9 +478,14 @@ class DeviceScene(object):
                     self.pull(pa, n)
                 pa.__dict__['_device_newer'].clear()
             hist, parity = self.H, self.parity
+            shape = (self.n_rigid, self.ks)
             self._build_static()
-            self.H, self.parity = hist, parity
-            self._refresh_structs()
+            # the contact history survives a change of the static tables, but
+            # not one of the particle set (remove_particles / add_particles):
+            # its rows are per particle
+            if shape == (self.n_rigid, self.ks):
+                self.H, self.parity = hist, parity
+                self._refresh_structs()
 
     def mark_device_newer(self):
         for pa in self.rigid:

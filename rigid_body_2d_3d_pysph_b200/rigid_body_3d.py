@@ -34,11 +34,13 @@ class GTVFRigidBody3DStep(IntegratorStep):
 
 class RK2RigidBody3DStep(IntegratorStep):
     """rigid_body_3d.py:406-575, run under EPEC sequencing.  The reference
-    saves only body 0's angular momentum (``ang_mom0[j] = ang_mom[j]``,
-    :415, quirk Q7); ``fix_q7=True`` (default) saves every body's."""
+    saves only the angular momentum of the first body of an array
+    (``ang_mom0[j] = ang_mom[j]``, :415, quirk Q7) and that is the default
+    here too (as in ``DeviceScene.rk2_step``); ``fix_q7=True`` saves every
+    body's."""
     kind = 'rk2'
 
-    def __init__(self, fix_q7=True):
+    def __init__(self, fix_q7=False):
         self.fix_q7 = fix_q7
 
 

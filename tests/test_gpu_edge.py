@@ -192,6 +192,36 @@ def test_split_source_bodies_and_long_lists():
     assert sc.read_counters()['active_slots'] > 0
 
 
+def test_more_source_bodies_than_hash_slots_in_one_tile():
+    """A hollow frame (124 particles = one chunk) around a raft of 2x2 bodies:
+    the chunk's box holds more than 128 distinct source bodies, i.e. more
+    than k_neighbours' tile hash has slots (bodies share a group and come out
+    as interleaved runs).  The chunk must be flagged as split (bit 30 of
+    nbr_cnt) so that no partial run is prefiltered on its own, and the
+    forces must still be the oracle's; the outer ring of small bodies
+    touches the frame."""
+    dx = 0.05
+    n = 32
+    k = np.arange(n)
+    fx = np.r_[k, k, np.zeros(n - 2), np.full(n - 2, n - 1)] * dx
+    fy = np.r_[np.zeros(n), np.full(n, n - 1), k[1:-1], k[1:-1]] * dx
+    frame = (fx, fy, np.zeros(fx.size))
+    # 2x2 bodies on a 13 x 13 lattice inside the frame: 0.95 dx from it on
+    # the left and at the bottom, 2.2 dx apart from one another
+    pitch = 2.2 * dx
+    bodies = [frame]
+    for a in range(13):
+        for b in range(13):
+            bodies.append(_block2d(2, 2, dx, 1.95 * dx + a * pitch,
+                                   1.95 * dx + b * pitch))
+    arrays, s = _make(2, bodies, None, dx, dx)
+    sc, g, o = _run_both(arrays, s, 2, 2e-5, 6)
+    cnt = sc.T['nbr_cnt'].cpu().numpy()
+    assert ((cnt[:fx.size] >> 30) & 1).all(), 'frame chunk not flagged split'
+    assert sc.read_counters()['active_slots'] > 0
+    assert np.abs(o.fx[:fx.size]).max() > 0
+
+
 def test_device_boundary_identification_equals_host():
     """the device setup path gives the host evaluator's
     is_boundary (exactly) and normals (to rounding) on a 3-D body + tank and

@@ -9,7 +9,8 @@ from rigid_body_2d_3d_pysph_b200.compat.output import load_scene
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
 CASES = ['free2d_gtvf2d', 'free2d_gtvf3d', 'wall2d', 'wall2d_planar',
-         'wall2d_rest', 'wall2d_normal', 'collide2d', 'cubes3d', 'rk2_3d']
+         'wall2d_rest', 'wall2d_normal', 'collide2d', 'cubes3d', 'rk2_3d',
+         'rk2_3d_nb2']
 
 # dense slot arrays compared against the reference (ti_* excluded: quirk Q5)
 SLOT_PROPS = ['contact_force_normal_x', 'contact_force_normal_y',
