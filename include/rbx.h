@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RBX_VERSION 301 /* 0.3.1 */
+#define RBX_VERSION 400 /* 0.4.0 */
 
 typedef enum {
   RBX_OK = 0,
@@ -183,6 +183,33 @@ typedef struct {
   float *pos32;
   int32_t *clist;
   double origin[3];
+  /* Sparse outputs of the contact evaluation (all optional, NULL = every
+   * output is written for every particle at every evaluation).  At config 5
+   * about 1 % of the particles are in contact; everything else carries
+   * fx, fy, fz = m g and an empty history, step after step.  The evaluation
+   * then only writes what changes:
+   *   alist_out / acount_out: particles that came out of THIS evaluation with
+   *     at least one slot in contact (they own rows of hist_*_out and a
+   *     non-trivial force); alist_prev / acount_prev: the same of the previous
+   *     evaluation.  Before the pair kernels run, fx, fy, fz of alist_prev are
+   *     reset to m g and hist_key_out of the old content of alist_out (two
+   *     evaluations ago: the last owner of these rows) to "empty".  The
+   *     caller swaps the two together with the history buffers.
+   *   RBX_PARAM_DENSE_OUT makes one evaluation write every particle (first
+   *     evaluation, or after the host changed fx / m / the history).
+   *   body_tag[n_bodies]: set to 1 for a body with a particle in contact;
+   *     rbx_reduce_bodies sums the particles of tagged bodies only (and clears
+   *     (the next evaluation clears the tags of alist_prev), every other body
+   *     gets force = total_mass * gravity, torque = 0.
+   *   aux32[2 n_rigid] = {m / rho, spacing0 of the body} as floats for the
+   *     FP32 first pass (instead of m, rho, body, spacing0[body]).
+   *   h_uniform > 0: every particle has this h (pos32.w without loading h).  */
+  int32_t *alist_out, *alist_prev;
+  uint32_t *acount_out, *acount_prev;
+  int32_t *body_tag;
+  const float *aux32;
+  double h_uniform;
+  double gravity[3];  /* = RbxParams.gx, gy, gz (force of an untagged body) */
 } RbxScene;
 
 typedef struct {
@@ -199,6 +226,13 @@ typedef struct {
 } RbxParams;
 
 #define RBX_PARAM_EXACT 1  /* evaluate every slot in FP64 (no FP32 first pass) */
+#define RBX_PARAM_BODY_VEL 2 /* velocities of rigid particles are not read from
+                                u, v, w but formed where needed as
+                                vcm + omega x (R_prev r0) (stage 1 of the GTVF
+                                step, rigid_body_3d.py:62-95, fused after the
+                                drift): rbx_gtvf_step sets it and writes u, v,
+                                w once, at the end of the step              */
+#define RBX_PARAM_DENSE_OUT 4 /* see RbxScene.alist_out                       */
 
 /* Optional per-slot diagnostics of one contact evaluation, slot-major
  * [RBX_MAX_KEYS][n_rigid]; any pointer may be NULL.  Used by parity tests
@@ -302,7 +336,7 @@ int rbx_contact_canelas(const RbxScene *scene, const RbxCells *cells,
 
 /* SumUpExternalForces.reduce (rigid_body_common.py:128-175): fx,fy,fz,x,y,z
  * -> force[3nb], torque[3nb], one warp per body, fixed order
- * (deterministic).                                                        */
+ * (deterministic).  With RbxScene.body_tag: tagged bodies only (see there). */
 int rbx_reduce_bodies(const RbxScene *scene, void *stream);
 
 /* GTVFRigidBody{3D,2D}Step.py_stage1 / py_stage3 (rigid_body_3d.py:41-60,
@@ -371,7 +405,9 @@ int rbx_boundary_identify(const RbxPoints *pts, const RbxCells *cells, int dim,
 /* Whole GTVF step [upstream GTVFIntegrator.one_timestep, SURVEY App. C-6]:
  * kick, drift, pose, cells_build, contact, reduce, kick, velocities.
  * `src` = the source points (contact_force_is_boundary == 1) to bin.
- * flags: bit0 = skip the final particle-velocity write (state not observed) */
+ * flags: bit0 = skip the final particle-velocity / boundary-normal write
+ * (inside a batch of steps nothing reads them: stage 1 of the next step
+ * overwrites the velocities, and the normals are a function of R alone)     */
 int rbx_gtvf_step(const RbxScene *scene, const RbxPoints *src,
                   const RbxCells *cells, const RbxParams *params,
                   void *workspace, size_t workspace_bytes, int flags,

@@ -21,6 +21,8 @@ STATUS_GRID_COARSENED = 8
 STATUS_LVC_OVERFLOW = 16
 STATUS_PAIR_OVERFLOW = 32
 PARAM_EXACT = 1
+PARAM_BODY_VEL = 2
+PARAM_DENSE_OUT = 4
 
 POSE_POS, POSE_VEL, POSE_VEL_PREV, POSE_NORMALS = 1, 2, 4, 8
 
@@ -60,7 +62,10 @@ _SCENE_PTRS = ['x', 'y', 'z', 'u', 'v', 'w', 'h', 'm', 'rho', 'dem_id',
 
 class RbxScene(ctypes.Structure):
     _fields_ = [(n, c_i32) for n in _SCENE_INTS] + \
-               [(n, c_vp) for n in _SCENE_PTRS] + [('origin', c_f64 * 3)]
+               [(n, c_vp) for n in _SCENE_PTRS] + [('origin', c_f64 * 3)] + \
+               [(n, c_vp) for n in ('alist_out', 'alist_prev', 'acount_out',
+                                    'acount_prev', 'body_tag', 'aux32')] + \
+               [('h_uniform', c_f64), ('gravity', c_f64 * 3)]
 
 
 _DEM_PTRS = ['x', 'y', 'z', 'u', 'v', 'w', 'wx', 'wy', 'wz', 'h', 'm', 'rad_s',

@@ -130,6 +130,16 @@ __global__ void __launch_bounds__(128, 8) k_reduce(RbxScene S) {
   const int lane = threadIdx.x & 31;
   if (warp >= S.n_bodies) return;
   const int b = warp;
+  // no particle of this body is in contact: every f_i = m_i g, so
+  // F = M g and the torque of a uniform field about the centre of mass is 0
+  // (the dense sum gives rounding noise, 1e-16 of its terms)
+  if (S.body_tag && S.body_tag[b] == 0) {
+    if (lane < 3) {
+      S.force[3 * b + lane] = S.total_mass[b] * S.gravity[lane];
+      S.torque[3 * b + lane] = 0.;
+    }
+    return;
+  }
   double v6[6] = {0, 0, 0, 0, 0, 0};
   const int q0 = S.chunk_start[S.body_chunk[b]], q1 = S.chunk_start[S.body_chunk[b + 1]];
   const double cx = S.xcm[3 * b], cy = S.xcm[3 * b + 1], cz = S.xcm[3 * b + 2];
@@ -201,48 +211,40 @@ __global__ void k_rk2(RbxScene S, int stage, double dt, int fix_q7, double skin)
   check_displacement(S, b, skin);
 }
 
-__global__ void k_pose(RbxScene S, int flags) {
+__global__ void __launch_bounds__(256) k_pose(RbxScene S, int flags) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= S.n_rigid) return;
   const int b = S.body[p];
   const int i9 = 9 * b, i3 = 3 * b;
   const double x0 = S.dx0[p], y0 = S.dy0[p], z0 = S.dz0[p];
-  double R[9];
-#pragma unroll
-  for (int k = 0; k < 9; k++) R[k] = S.R[i9 + k];
   if (flags & RBX_POSE_VEL) {
-    double Rv[9];
-    if (flags & RBX_POSE_VEL_PREV) {
-#pragma unroll
-      for (int k = 0; k < 9; k++) Rv[k] = S.R_prev[i9 + k];
-    } else {
-#pragma unroll
-      for (int k = 0; k < 9; k++) Rv[k] = R[k];
-    }
-    const double dx = (Rv[0] * x0 + Rv[1] * y0 + Rv[2] * z0);
-    const double dy = (Rv[3] * x0 + Rv[4] * y0 + Rv[5] * z0);
-    const double dz = (Rv[6] * x0 + Rv[7] * y0 + Rv[8] * z0);
-    const double o0 = S.omega[i3], o1 = S.omega[i3 + 1], o2 = S.omega[i3 + 2];
-    const double du = o1 * dz - o2 * dy;
-    const double dv = o2 * dx - o0 * dz;
-    const double dw = o0 * dy - o1 * dx;
-    S.u[p] = S.vcm[i3] + du;
-    S.v[p] = S.vcm[i3 + 1] + dv;
-    S.w[p] = S.vcm[i3 + 2] + dw;
+    const double *Rv = ((flags & RBX_POSE_VEL_PREV) ? S.R_prev : S.R) + i9;
+    double u, v, w;
+    rbx_point_velocity(Rv, S.omega + i3, S.vcm + i3, x0, y0, z0, u, v, w);
+    S.u[p] = u;
+    S.v[p] = v;
+    S.w[p] = w;
   }
-  if (flags & RBX_POSE_POS) {
-    const double dx = (R[0] * x0 + R[1] * y0 + R[2] * z0);
-    const double dy = (R[3] * x0 + R[4] * y0 + R[5] * z0);
-    const double dz = (R[6] * x0 + R[7] * y0 + R[8] * z0);
-    const double xn = S.xcm[i3] + dx, yn = S.xcm[i3 + 1] + dy, zn = S.xcm[i3 + 2] + dz;
-    S.x[p] = xn;
-    S.y[p] = yn;
-    S.z[p] = zn;
-    // FP32 copy for the first pass of the contact evaluation (k_filter)
-    if (S.pos32)
-      reinterpret_cast<float4 *>(S.pos32)[p] =
-          make_float4((float)(xn - S.origin[0]), (float)(yn - S.origin[1]),
-                      (float)(zn - S.origin[2]), (float)S.h[p]);
+  if (flags & (RBX_POSE_POS | RBX_POSE_NORMALS)) {
+    double R[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) R[k] = S.R[i9 + k];
+    if (flags & RBX_POSE_POS) {
+      const double dx = (R[0] * x0 + R[1] * y0 + R[2] * z0);
+      const double dy = (R[3] * x0 + R[4] * y0 + R[5] * z0);
+      const double dz = (R[6] * x0 + R[7] * y0 + R[8] * z0);
+      const double xn = S.xcm[i3] + dx, yn = S.xcm[i3 + 1] + dy, zn = S.xcm[i3 + 2] + dz;
+      S.x[p] = xn;
+      S.y[p] = yn;
+      S.z[p] = zn;
+      // FP32 copy for the first pass of the contact evaluation (k_filter)
+      if (S.pos32) {
+        const float hf = S.h_uniform > 0. ? (float)S.h_uniform : (float)S.h[p];
+        reinterpret_cast<float4 *>(S.pos32)[p] =
+            make_float4((float)(xn - S.origin[0]), (float)(yn - S.origin[1]),
+                        (float)(zn - S.origin[2]), hf);
+      }
+    }
     if ((flags & RBX_POSE_NORMALS) && S.normal && S.is_boundary && S.is_boundary[p] == 1) {
       const double n0 = S.normal0[3 * p], n1 = S.normal0[3 * p + 1], n2 = S.normal0[3 * p + 2];
       S.normal[3 * p] = (R[0] * n0 + R[1] * n1 + R[2] * n2);
@@ -351,17 +353,23 @@ extern "C" int rbx_gtvf_step(const RbxScene *scene, const RbxPoints *src, const 
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
   if ((rc = launch_bodies(scene, 8 | 4, params->dt, params->skin, st))) return rc;
-  if ((rc = rbx_pose_particles(scene, RBX_POSE_POS | RBX_POSE_VEL | RBX_POSE_VEL_PREV |
-                                          RBX_POSE_NORMALS, stream))) return rc;
+  // Positions only.  The stage-1 velocities (post-kick omega, pre-drift R)
+  // are needed for the ~1 % of the particles in contact, which the contact
+  // law forms itself (RBX_PARAM_BODY_VEL); u, v, w and the rotated normals
+  // are written once, at the end of the step.
+  if (!scene->R_prev) return RBX_ERR_INVALID;
+  RbxParams par = *params;
+  par.flags |= RBX_PARAM_BODY_VEL;
+  if ((rc = rbx_pose_particles(scene, RBX_POSE_POS, stream))) return rc;
   if ((rc = rbx_cells_build(src, cells, params->reach, scene->status, workspace,
                             workspace_bytes, stream))) return rc;
-  if ((rc = rbx_contact_mofidi(scene, cells, params, nullptr, stream))) return rc;
+  if ((rc = rbx_contact_mofidi(scene, cells, &par, nullptr, stream))) return rc;
   // reduce (k_reduce, warp per body) and kick (k_bodies, thread per body)
   // are two launches: with the kick's divisions on lane 0 of every reduce
   // warp, the warp sat on its slot three times longer than its loads take
   if ((rc = launch_bodies(scene, 1 | 2, params->dt, 0., st))) return rc;
   if (!(flags & 1))
-    if ((rc = rbx_pose_particles(scene, RBX_POSE_VEL, stream))) return rc;
+    if ((rc = rbx_pose_particles(scene, RBX_POSE_VEL | RBX_POSE_NORMALS, stream))) return rc;
   return RBX_OK;
 }
 

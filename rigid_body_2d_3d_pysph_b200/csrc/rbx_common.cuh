@@ -111,6 +111,24 @@ __device__ __forceinline__ double rbx_rsqrt(double x) {
   return fma(fma(e, 0.375, 0.5), y * e, y);
 }
 
+// stage1 / stage3 of the body particles (rigid_body_3d.py:62-95, 192-225):
+// v = vcm + omega x (R r0).  One definition for k_pose and for the contact
+// law, which forms the velocities of the few particles in contact itself
+// (RBX_PARAM_BODY_VEL) -- the same instruction sequence, the same bits.
+__device__ __forceinline__ void rbx_point_velocity(const double *Rv, const double *om,
+                                                   const double *vc, double x0, double y0,
+                                                   double z0, double &u, double &v, double &w) {
+  const double dx = (Rv[0] * x0 + Rv[1] * y0 + Rv[2] * z0);
+  const double dy = (Rv[3] * x0 + Rv[4] * y0 + Rv[5] * z0);
+  const double dz = (Rv[6] * x0 + Rv[7] * y0 + Rv[8] * z0);
+  const double du = om[1] * dz - om[2] * dy;
+  const double dv = om[2] * dx - om[0] * dz;
+  const double dw = om[0] * dy - om[1] * dx;
+  u = vc[0] + du;
+  v = vc[1] + dv;
+  w = vc[2] + dw;
+}
+
 __device__ __forceinline__ void rbx_prefetch_l2(const void *p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }

@@ -680,8 +680,19 @@ finalize_slots(const RbxScene *Sp, const RbxParams *Pp, const RbxDiag *Dp,
     double ovl_out = 0., ft0 = 0., ft1 = 0., ft2 = 0.;
     const double overlap = spacing0 - dist;
     if (overlap > 0. && overlap != spacing0) {
+      // velocity of particle q: u, v, w, or for a rigid particle under
+      // RBX_PARAM_BODY_VEL the stage-1 velocity formed from its body
+      auto velocity = [&](int q, double &uq, double &vq, double &wq) {
+        if ((P.flags & RBX_PARAM_BODY_VEL) && q < S.n_rigid) {
+          const int bq = S.body[q];
+          rbx_point_velocity(S.R_prev + 9 * bq, S.omega + 3 * bq, S.vcm + 3 * bq, S.dx0[q],
+                             S.dy0[q], S.dz0[q], uq, vq, wq);
+        } else {
+          uq = S.u[q]; vq = S.v[q]; wq = S.w[q];
+        }
+      };
       double vxs = 0., vys = 0., vzs = 0.;
-      if (gmin >= 0) { vxs = S.u[gmin]; vys = S.v[gmin]; vzs = S.w[gmin]; }
+      if (gmin >= 0) velocity(gmin, vxs, vys, vzs);
       // previous state of this slot
       double dl0 = 0., dl1 = 0., dl2 = 0., fn0 = 0., fn1 = 0., fn2 = 0.;
       for (int s2 = 0; s2 < S.ks; s2++) {
@@ -695,7 +706,8 @@ finalize_slots(const RbxScene *Sp, const RbxParams *Pp, const RbxDiag *Dp,
         }
       }
       const double md = S.m[p];
-      const double ud = S.u[p], vd = S.v[p], wd = S.w[p];
+      double ud, vd, wd;
+      velocity(p, ud, vd, wd);
       const double vij_x = ud - vxs, vij_y = vd - vys, vij_z = wd - vzs;
       const double vn = vij_x * nx + vij_y * ny + vij_z * nz;
       ovl_out = overlap;
@@ -999,6 +1011,11 @@ k_slots(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
     }
     if (nk > 0) finalize_slots(&S, &P, &D, acc, ovf, nk, p, tid, (cnt_raw & kSplitBit) != 0, &so);
     nactive += so.nactive;
+    if (so.nactive && S.alist_out) {
+      // owns history rows and a force that is not m g: see RbxScene.alist_out
+      S.alist_out[atomicAdd(S.acount_out, 1u)] = p;
+      if (S.body_tag) S.body_tag[S.body[p]] = 1;
+    }
     if (so.nout < S.ks) S.hist_key_out[(size_t)so.nout * n_rigid + p] = -1;
     if (D.key)
       for (int k2 = so.ki; k2 < RBX_MAX_KEYS; k2++) D.key[(size_t)k2 * n_rigid + p] = -1;
@@ -1069,6 +1086,7 @@ k_filter(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P
   const float4 *__restrict__ pos = reinterpret_cast<const float4 *>(S.pos32);
   const int nitems = (S.n_rigid + 31) / 32;
   unsigned npairs = 0;
+  const bool dense_out = !S.alist_out || (P.flags & RBX_PARAM_DENSE_OUT);
   constexpr float kU = 5.9604645e-8f;            // 2^-24
   constexpr float kSqrt3 = 1.7320509f;
   const float Lr = (float)((P.reach + P.skin) * (1. + 1e-6));
@@ -1086,8 +1104,14 @@ k_filter(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P
       const int nlist = cnt_raw & (kSplitBit - 1);
       const bool all = (cnt_raw & kSplitBit) != 0;   // split bodies: partial sums
       const float4 me = pos[p];
-      const float s0 = (float)S.spacing0[S.body[p]];
-      const float vol = (float)(S.m[p] / S.rho[p]);
+      float s0, vol;
+      if (S.aux32) {
+        const float2 a = reinterpret_cast<const float2 *>(S.aux32)[p];
+        vol = a.x; s0 = a.y;
+      } else {
+        s0 = (float)S.spacing0[S.body[p]];
+        vol = (float)(S.m[p] / S.rho[p]);
+      }
       // error coefficients of this particle
       const float E = fmaxf(fmaxf(fabsf(me.x), fabsf(me.y)), fabsf(me.z)) + Lr;
       const float ex = 2.1f * kU * E;
@@ -1174,8 +1198,9 @@ k_filter(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P
         if (e0 + 1 < nlist) entry(qb, sb);
         qa = la; qb = lb; sa = ga; sb = gb; la = na; lb = nb;
       }
-      if (mask == 0u) {
+      if (mask == 0u && dense_out) {
         // nothing can be in contact: BodyForce alone (:122-125), no history
+        // (sparse outputs: both are already in place, RbxScene.alist_out)
         const double md = S.m[p];
         S.fx[p] = md * P.gx; S.fy[p] = md * P.gy; S.fz[p] = md * P.gz;
         S.hist_key_out[p] = -1;
@@ -1199,6 +1224,26 @@ k_filter(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) np_ += __shfl_xor_sync(0xffffffffu, np_, o);
   if (lane == 0 && np_) atomicAdd(&S.counters[0], (unsigned long long)np_);
+}
+
+// Sparse outputs (RbxScene.alist_out): before the pair kernels run, take back
+// what the last two evaluations left behind -- the force of the particles
+// that were in contact at the previous evaluation becomes m g again
+// (BodyForce, rigid_body_common.py:122-125), their bodies lose the tag, and
+// the history rows of the out buffer, last written two evaluations ago, read
+// "empty" (the zeroed slot of :1014-1027).
+__global__ void k_sparse_reset(RbxScene S, RbxParams P) {
+  const unsigned n_out = *S.acount_out, n_prev = *S.acount_prev;
+  const unsigned n = n_out > n_prev ? n_out : n_prev;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (i < n_out) S.hist_key_out[S.alist_out[i]] = -1;
+    if (i < n_prev) {
+      const int p = S.alist_prev[i];
+      const double md = S.m[p];
+      S.fx[p] = md * P.gx; S.fy[p] = md * P.gy; S.fz[p] = md * P.gz;
+      if (S.body_tag) S.body_tag[S.body[p]] = 0;
+    }
+  }
 }
 
 // pos32 of the particles [first, first + n)
@@ -1281,6 +1326,13 @@ extern "C" int rbx_contact_slots(const RbxScene *scene, const RbxCells *cells,
   int ng = rbx_blocks(scene->n_rigid, kSlotsCta);
   const int resident = sms * RBX_SLOTS_MINB - 1;
   if (ng > resident) ng = resident;
+  if (scene->alist_out) {
+    if (!scene->alist_prev || !scene->acount_out || !scene->acount_prev) return RBX_ERR_INVALID;
+    k_sparse_reset<<<sms * 2, 256, 0, st>>>(*scene, *params);
+    cudaMemsetAsync(scene->acount_out, 0, sizeof(uint32_t), st);
+    if ((params->flags & RBX_PARAM_DENSE_OUT) && scene->body_tag)
+      cudaMemsetAsync(scene->body_tag, 0, sizeof(int32_t) * (size_t)scene->n_bodies, st);
+  }
   if (fast) {
     cudaMemsetAsync(&scene->counters[6], 0, sizeof(unsigned long long), st);
     int nf = rbx_blocks(scene->n_rigid, 32);

@@ -288,6 +288,24 @@ class DeviceScene(object):
                 'fn': torch.zeros(3 * self.ks * nr, dtype=f64, device=dev)})
         self.status = torch.zeros(1, dtype=i32, device=dev)
         self.counters = torch.zeros(8, dtype=torch.int64, device=dev)
+        # sparse outputs (RbxScene.alist_out): the particles in contact after
+        # the last two evaluations, one list per history buffer; tags of the
+        # bodies they belong to; {m / rho, spacing0} as floats for k_filter
+        self.A = [torch.zeros(nr, dtype=i32, device=dev) for _ in range(2)]
+        self.acount = torch.zeros(2, dtype=i32, device=dev)
+        self.T['body_tag'] = torch.zeros(max(self.n_bodies, 1), dtype=i32,
+                                         device=dev)
+        aux = torch.zeros(2 * nr, dtype=torch.float32, device=dev)
+        if self.n_rigid:
+            aux[0:2 * self.n_rigid:2] = (self.P['m'][:self.n_rigid] /
+                                         self.P['rho'][:self.n_rigid]).float()
+            aux[1:2 * self.n_rigid:2] = \
+                self.B['spacing0'][self.P['body'].long()].float()
+        self.T['aux32'] = aux
+        # evaluations that still have to write every particle (fx = m g and
+        # an empty history where nothing is in contact) before the sparse
+        # writes can rely on what is in place
+        self._dense_pending = 2
         # ---- cell list over the sources ----------------------------------
         self._alloc_cells(max(self.n_src, 1), self.T['src_index'])
         self._refresh_structs()
@@ -343,6 +361,9 @@ class DeviceScene(object):
             setattr(s, n, _ptr(T[n]))
         for k in range(3):
             s.origin[k] = self.origin[k]
+            s.gravity[k] = self.g[k]
+        s.h_uniform = self.h_uniform
+        s.body_tag, s.aux32 = _ptr(T['body_tag']), _ptr(T['aux32'])
         for n in ['total_mass', 'izz', 'spacing0', 'xcm', 'vcm', 'ang_mom',
                   'omega', 'force', 'torque', 'R', 'R_prev', 'xcm0', 'vcm0',
                   'ang_mom0', 'R0']:
@@ -363,6 +384,10 @@ class DeviceScene(object):
                 _ptr(hin['key']), _ptr(hin['dlt']), _ptr(hin['fn'])
             c.hist_key_out, c.hist_dlt_out, c.hist_fn_out = \
                 _ptr(hout['key']), _ptr(hout['dlt']), _ptr(hout['fn'])
+            # A[k] / acount[k] go with history buffer k
+            c.alist_out, c.alist_prev = _ptr(self.A[1 - par]), _ptr(self.A[par])
+            c.acount_out = self.acount.data_ptr() + 4 * (1 - par)
+            c.acount_prev = self.acount.data_ptr() + 4 * par
             self._scene[par] = c
         self._src = self.points(self.T['src_index'])
         c = RbxCells()
@@ -398,10 +423,28 @@ class DeviceScene(object):
         return p
 
     def params(self, dt):
+        flags = _lib.PARAM_EXACT if self.exact else 0
+        if self._dense_pending > 0:
+            flags |= _lib.PARAM_DENSE_OUT
         return RbxParams(self.radius_scale, self.kr, self.kf,
                          self.fric_coeff, self.g[0], self.g[1], self.g[2],
                          float(dt), self.reach, self.h_uniform, self.skin,
-                         _lib.PARAM_EXACT if self.exact else 0, 0)
+                         flags, 0)
+
+    def _evaluated(self):
+        """One contact evaluation has been issued: the history buffers (and
+        the lists that go with them) swap roles."""
+        self.parity ^= 1
+        self._reduce_dense = False
+        if self._dense_pending > 0:
+            self._dense_pending -= 1
+
+    def invalidate_outputs(self):
+        """The host changed forces, masses or the history behind the back of
+        the sparse writes: the next two evaluations (one per history buffer)
+        write every particle."""
+        self._dense_pending = 2
+        self.acount.zero_()
 
     def force_rebuild(self):
         """Neighbour lists must be rebuilt at the next force evaluation."""
@@ -470,6 +513,7 @@ class DeviceScene(object):
                 if name in ('x', 'y', 'z', 'h'):
                     refresh32 = True
             touched.clear()
+            self.invalidate_outputs()
         if refresh32 and not rebuild:
             self.pos32_refresh()
         if rebuild:
@@ -521,7 +565,7 @@ class DeviceScene(object):
             ctypes.byref(self.scene), ctypes.byref(self._cells),
             ctypes.byref(p), ctypes.byref(diag) if diag is not None else None,
             self.stream), 'rbx_contact_mofidi')
-        self.parity ^= 1
+        self._evaluated()
 
     def contact_canelas(self, dt, Cn=1.4e-5):
         """BodyForce + RigidBodyCanelasRigidRigid / RigidBodyCanelasRigidWall
@@ -583,11 +627,19 @@ class DeviceScene(object):
             ctypes.byref(self.scene), ctypes.byref(t['cells']),
             ctypes.byref(p), ctypes.byref(t['struct']), self.stream),
             'rbx_contact_canelas')
+        self._reduce_dense = True
+        self.invalidate_outputs()       # fx was written densely, untagged
         self.mark_device_newer()
 
     def reduce_bodies(self):
-        _lib.check(self.lib.rbx_reduce_bodies(ctypes.byref(self.scene),
-                                              self.stream), 'reduce')
+        sc = self.scene
+        if getattr(self, '_reduce_dense', False):
+            # forces written by something that does not tag the bodies in
+            # contact (the Canelas kernel): sum every body's particles
+            sc = RbxScene.from_buffer_copy(sc)
+            sc.body_tag = None
+        _lib.check(self.lib.rbx_reduce_bodies(ctypes.byref(sc), self.stream),
+                   'reduce')
 
     def gtvf_kick(self, dt):
         _lib.check(self.lib.rbx_gtvf_kick(ctypes.byref(self.scene), float(dt),
@@ -613,21 +665,26 @@ class DeviceScene(object):
             ctypes.byref(self.scene), ctypes.byref(self._src),
             ctypes.byref(self._cells), ctypes.byref(p), _ptr(self.workspace),
             self.workspace.numel(), int(flags), self.stream), 'rbx_gtvf_step')
-        self.parity ^= 1
+        self._evaluated()
 
     def gtvf_step(self, dt, nsteps=1, graph=False):
         """nsteps x GTVFIntegrator.one_timestep on the device."""
         self.push_touched()
-        p = self.params(dt)
         # The stage-3 particle velocities of a step are overwritten by stage 1
-        # of the next one before anything reads them: inside a batch only the
-        # last step writes them (flag bit 0 of rbx_gtvf_step).
-        if graph and nsteps >= 4:
-            self._run_graph(p, nsteps)
-            self.pose(_lib.POSE_VEL)
+        # of the next one before anything reads them, and the boundary
+        # normals are a function of R alone: inside a batch only the last
+        # step writes them (flag bit 0 of rbx_gtvf_step).
+        left = nsteps
+        while left and self._dense_pending:     # never captured in a graph
+            self._gtvf_step_call(self.params(dt), flags=0 if left == 1 else 1)
+            left -= 1
+        p = self.params(dt)
+        if graph and left >= 4:
+            self._run_graph(p, left)
+            self.pose(_lib.POSE_VEL | _lib.POSE_NORMALS)
         else:
-            for k in range(nsteps):
-                self._gtvf_step_call(p, flags=0 if k == nsteps - 1 else 1)
+            for k in range(left):
+                self._gtvf_step_call(p, flags=0 if k == left - 1 else 1)
         self.steps_done += nsteps
         self.mark_device_newer()
 
@@ -793,6 +850,7 @@ class DeviceScene(object):
         hk[:, o:o + n] = -1
         hd[:, :, o:o + n] = 0.
         hf[:, :, o:o + n] = 0.
+        self.invalidate_outputs()
         hk[:k, o:o + n] = self._t(key, torch.int32)
         hd[:, :k, o:o + n] = self._t(np.asarray(dlt, dtype=np.float64),
                                      torch.float64)

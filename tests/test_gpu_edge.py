@@ -212,9 +212,11 @@ def test_more_source_bodies_than_hash_slots_in_one_tile():
     bodies = [frame]
     for a in range(13):
         for b in range(13):
-            bodies.append(_block2d(2, 2, dx, 1.95 * dx + a * pitch,
-                                   1.95 * dx + b * pitch))
+            bodies.append(_block2d(2, 2, dx, 0.95 * dx + a * pitch,
+                                   0.95 * dx + b * pitch))
     arrays, s = _make(2, bodies, None, dx, dx)
+    # (the SPH boundary identification finds no surface on a 2x2 block)
+    arrays[0].contact_force_is_boundary[:] = 1.
     sc, g, o = _run_both(arrays, s, 2, 2e-5, 6)
     cnt = sc.T['nbr_cnt'].cpu().numpy()
     assert ((cnt[:fx.size] >> 30) & 1).all(), 'frame chunk not flagged split'
