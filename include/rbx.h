@@ -177,9 +177,10 @@ typedef struct {
    * particles), rbx_halo_unpack, rbx_pos32_refresh, and for the static
    * particles by rbx_contact_neighbours on a rebuild.  A first pass sums
    * every (particle, source body) slot in FP32 with a running error bound
-   * and proves most of them out of contact; clist[2 n_rigid] receives
-   * {work item, bit mask of the runs that could not be excluded} and only
-   * those are evaluated by the exact FP64 code.  counters[6] = entries.     */
+   * and proves most of them out of contact; clist[4 n_rigid] receives
+   * {work item, bit mask of the runs that could not be excluded, first entry
+   * | ordinal << 20 of the first such run, last entry of the last one} and
+   * only those are evaluated by the exact FP64 code.  counters[6] = entries. */
   float *pos32;
   int32_t *clist;
   double origin[3];

@@ -36,7 +36,7 @@ class Solver(object):
         # capacities / tuning of the device scene (device.py)
         self.ks = kwargs.pop('ks', 8)
         self.list_cap = kwargs.pop('list_cap', 96)
-        self.skin_factor = kwargs.pop('skin_factor', 0.05)
+        self.skin_factor = kwargs.pop('skin_factor', 0.075)
         self.use_graph = kwargs.pop('use_graph', True)
         # one damping coefficient for every (body, body) pair instead of the
         # reference's dense nb x tnb `eta` table (large scenes)

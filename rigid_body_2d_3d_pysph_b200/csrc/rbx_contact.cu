@@ -818,11 +818,15 @@ k_slots(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
   // three dependent DRAM round trips and nothing to overlap them with)
   int p_next = -1, cnt_next = 0, t_next = 0;
   unsigned mask_next = 0xffffffffu;
+  int first_next = 0, last_next = 0x7fffffff;   // COMPACT: entries to walk
   auto fetch_item = [&](int i) {
     p_next = -1;
     if (i < nwork) {
       t_next = i;
-      if (COMPACT) { t_next = S.clist[2 * i]; mask_next = (unsigned)S.clist[2 * i + 1]; }
+      if (COMPACT) {
+        const int4 c = reinterpret_cast<const int4 *>(S.clist)[i];
+        t_next = c.x; mask_next = (unsigned)c.y; first_next = c.z; last_next = c.w;
+      }
       p_next = S.nbr_order[t_next];
       cnt_next = S.nbr_cnt_srt[t_next];
     }
@@ -834,11 +838,17 @@ k_slots(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
   const int p = p_next;
   const int cnt_raw = cnt_next;
   const unsigned run_mask = mask_next;
+  const int e_first = COMPACT ? (first_next & 0xfffff) : 0;
+  const int run_first = COMPACT ? (first_next >> 20) : 0;
+  const int e_last = last_next;
   if (item + gridDim.x < nitems) fetch_item((item + gridDim.x) * kSlotsCta + tid);
   else p_next = -1;
   const int tn = t_next;
   if (valid) {
-    const int nlist = cnt_raw & (kSplitBit - 1);
+    // COMPACT: only the entries from the first to the last run that the FP32
+    // pass kept (what lies outside was excluded and adds exactly nothing)
+    const int ebeg = e_first;
+    const int nlist = min(cnt_raw & (kSplitBit - 1), COMPACT ? e_last + 1 : 0x7fffffff);
     // partial slots of a split body and the slots of a diagnostics run are
     // all parked; otherwise only those that pass the contact prefilter
     const bool park_all = (cnt_raw & kSplitBit) != 0 || D.key != nullptr;
@@ -858,7 +868,7 @@ k_slots(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
     int qmin = -1;           // its global index
     bool touched = false;    // some entry passed the neighbour predicate
     int nk = 0;              // slots parked in shared memory
-    int run = 0;             // ordinal of the source-body run being read
+    int run = run_first;     // ordinal of the source-body run being read
     SlotOut so;
     so.cfx = so.cfy = so.cfz = 0.;
     so.nout = 0; so.ki = 0; so.st = 0u; so.nactive = 0u;
@@ -889,11 +899,11 @@ k_slots(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
     // gathered (L1/L2) while entries e, e + 1 are processed.
     static_assert(kLd >= 2 && kLd % 2 == 0, "kLd");
     int ql[kLd];
-    const int *cl = S.nbr_srt + t;
+    const int *cl = S.nbr_srt + t + (size_t)ebeg * n_rigid;
 #pragma unroll
-    for (int j = 0; j < kLd; j++) ql[j] = (2 + j < nlist) ? cl[(size_t)(2 + j) * n_rigid] : 0;
-    int qc0 = nlist > 0 ? cl[0] : 0;
-    int qc1 = nlist > 1 ? cl[n_rigid] : 0;
+    for (int j = 0; j < kLd; j++) ql[j] = (ebeg + 2 + j < nlist) ? cl[(size_t)(2 + j) * n_rigid] : 0;
+    int qc0 = ebeg < nlist ? cl[0] : 0;
+    int qc1 = ebeg + 1 < nlist ? cl[n_rigid] : 0;
     cl += (size_t)(2 + kLd) * n_rigid;
     double c0x, c0y, c0z, c0h = 0., c1x, c1y, c1z, c1h = 0.;
     {
@@ -969,7 +979,7 @@ k_slots(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
       return !COMPACT || ((run_mask >> (r < 31 ? r : 31)) & 1u) != 0u;
     };
 #pragma unroll 2
-    for (int e0 = 0; e0 < nlist; e0 += 2) {
+    for (int e0 = ebeg; e0 < nlist; e0 += 2) {
       // stage G for entries e0 + 2, e0 + 3; stage L for e0 + 2 + kLd, + 3 + kLd
       const int qn0 = ql[0], qn1 = ql[1];
       const int i0 = qn0 & 0x7fffffff, i1 = qn1 & 0x7fffffff;
@@ -1003,8 +1013,9 @@ k_slots(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
       rbx_prefetch_l2(S.x + p_next); rbx_prefetch_l2(S.y + p_next); rbx_prefetch_l2(S.z + p_next);
       rbx_prefetch_l2(S.h + p_next); rbx_prefetch_l2(S.m + p_next); rbx_prefetch_l2(S.rho + p_next);
       rbx_prefetch_l2(S.body + p_next);
-      const int *ln = S.nbr_srt + tn;
-      const int nl = cnt_next & (kSplitBit - 1);
+      const int fb = COMPACT ? (first_next & 0xfffff) : 0;
+      const int *ln = S.nbr_srt + tn + (size_t)fb * n_rigid;
+      const int nl = (cnt_next & (kSplitBit - 1)) - fb;
 #pragma unroll
       for (int k = 0; k < 2 + kLd; k++)
         if (k < nl) rbx_prefetch_l2(ln + (size_t)k * n_rigid);
@@ -1098,6 +1109,7 @@ k_filter(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P
     const int t = item * 32 + lane;
     const bool valid = t < S.n_rigid;
     unsigned mask = 0u;
+    int efirst = 0, elast = 0, rfirst = 0;
     if (valid) {
       const int p = S.nbr_order[t];
       const int cnt_raw = S.nbr_cnt_srt[t];
@@ -1131,6 +1143,7 @@ k_filter(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P
       float ax = 0.f, ay = 0.f, az = 0.f, w1 = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
       float wA = 0.f, SD = 0.f;
       int run = 0;
+      int ecur = 0, estart = 0;        // entry being read, first entry of its run
 
       auto entry = [&](int qc, const float4 sp) {
         const float dx = me.x - sp.x, dy = me.y - sp.y, dz = me.z - sp.z;
@@ -1173,8 +1186,15 @@ k_filter(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P
           const float rhs = s0sq * (wh * wh) * aahi;
           // w <= 1e-12: the slot has no normal, dist = 0, overlap == spacing0
           const bool drop = (wh < 0.99e-12f) || (lhs > 0.f && lhs * lhs > rhs);
-          if (!drop || all) mask |= 1u << (run < 31 ? run : 31);
+          if (!drop || all) {
+            // the exact pass starts at the first kept run and stops after
+            // the last one
+            if (mask == 0u) { efirst = estart; rfirst = run < 31 ? run : 31; }
+            elast = ecur;
+            mask |= 1u << (run < 31 ? run : 31);
+          }
           run++;
+          estart = ecur + 1;
           ax = ay = az = w1 = bx = by = bz = 0.f;
           wA = SD = 0.f;
         }
@@ -1188,13 +1208,15 @@ k_filter(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P
       int la = nlist > 2 ? cl[2 * n_rigid] : 0;
       int lb = nlist > 3 ? cl[3 * n_rigid] : 0;
       cl += 4 * n_rigid;
-      float4 sa = pos[qa & 0x7fffffff], sb = pos[qb & 0x7fffffff];
+      float4 sa = pos[(unsigned)qa & 0x7fffffffu], sb = pos[(unsigned)qb & 0x7fffffffu];
       for (int e0 = 0; e0 < nlist; e0 += 2) {
-        const float4 ga = pos[la & 0x7fffffff], gb = pos[lb & 0x7fffffff];
+        const float4 ga = pos[(unsigned)la & 0x7fffffffu], gb = pos[(unsigned)lb & 0x7fffffffu];
         const int na = (e0 + 4 < nlist) ? cl[0] : 0;
         const int nb = (e0 + 5 < nlist) ? cl[n_rigid] : 0;
         cl += 2 * n_rigid;
+        ecur = e0;
         entry(qa, sa);
+        ecur = e0 + 1;
         if (e0 + 1 < nlist) entry(qb, sb);
         qa = la; qb = lb; sa = ga; sb = gb; la = na; lb = nb;
       }
@@ -1215,8 +1237,8 @@ k_filter(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P
       base = __shfl_sync(0xffffffffu, base, 0);
       if (mask != 0u) {
         const int k = base + __popc(bal & ((1u << lane) - 1u));
-        S.clist[2 * k] = t;
-        S.clist[2 * k + 1] = (int)mask;
+        reinterpret_cast<int4 *>(S.clist)[k] =
+            make_int4(t, (int)mask, efirst | (rfirst << 20), elast);
       }
     }
   }

@@ -54,7 +54,7 @@ class DeviceScene(object):
     def __init__(self, arrays, rigid_names, boundary_names=(), dim=3,
                  kr=1e5, kf=1e3, fric_coeff=0.5, gx=0., gy=0., gz=0.,
                  planar=False, ks=8, radius_scale=3.0, eta_uniform=None,
-                 cap_cells=None, list_cap=96, skin_factor=0.05, device=None,
+                 cap_cells=None, list_cap=96, skin_factor=0.075, device=None,
                  exact=False):
         if not torch.cuda.is_available():
             raise _lib.RbxError('DeviceScene needs a CUDA device; the '
@@ -230,7 +230,7 @@ class DeviceScene(object):
         # centre of the scene and the compact list of the exact pass
         self.T['pos32'] = torch.zeros(4 * max(self.n_total, 1),
                                       dtype=torch.float32, device=dev)
-        self.T['clist'] = torch.zeros(2 * nr_, dtype=i32, device=dev)
+        self.T['clist'] = torch.zeros(4 * nr_, dtype=i32, device=dev)
         self.origin = [0., 0., 0.]
         if self.n_total:
             for k, n in enumerate('xyz'):
