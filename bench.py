@@ -33,6 +33,23 @@ DT = 1e-4
 KR, KF, MU = 1e5, 1e3, 0.5
 
 
+def host_cores():
+    """Cores this process may run on (the container's share, not the box's)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+_T0 = time.perf_counter()
+
+
+def note(msg):
+    """progress on stderr (stdout carries the one JSON line)"""
+    sys.stderr.write('[bench %7.1fs] %s\n' % (time.perf_counter() - _T0, msg))
+    sys.stderr.flush()
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
@@ -108,6 +125,8 @@ def run_reference(args, rank, world):
         return
     from oracle import rbo
     from rigid_body_2d_3d_pysph_b200.scenes import synthetic_pile
+    # torchrun exports OMP_NUM_THREADS=1 to every rank: ask for the cores
+    threads = rbo.set_num_threads(args.cpu_threads or host_cores())
     nb = args.cpu_bodies
     (body, wall), scheme, info = synthetic_pile(nb, seed=0)
     rbo.add_sparse_history(body, 4)
@@ -122,8 +141,8 @@ def run_reference(args, rank, world):
     n = info['n_body_particles']
     value = n * args.steps / dt
     sample = ('%d-body / %d-particle pile (same generator, seed 0), %d settle '
-              '+ %d warm-up + %d timed steps' %
-              (nb, n, settle, args.warmup, args.steps))
+              '+ %d warm-up + %d timed steps, %d OpenMP threads' %
+              (nb, n, settle, args.warmup, args.steps, threads))
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT,
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
@@ -135,16 +154,45 @@ def run_reference(args, rank, world):
                    'bounded sample named in cpu_baseline.sample'},
         'contact_pairs_per_s': float(counts[0]) / dt,
         'cpu_baseline': {'value': value, 'unit': UNIT,
-                         'cores': rbo.num_threads(), 'kind': 'port',
+                         'cores': threads, 'kind': 'port',
                          'sample': sample,
                          'note': 'PySPH cannot be installed (no network); '
                          'this is the C/OpenMP restatement of the reference '
-                         'step, validated against the reference\'s own '
-                         'Python methods (tests/golden)'},
+                         'step (gcc -O3 -fopenmp -ffp-contract=off), '
+                         'validated against the reference\'s own Python '
+                         'methods (tests/golden)'},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0,
                 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line))
+
+
+def build_scene(args, rank, world, bodies, halo_cap, dev):
+    """The pile through the package's public surface: scene generator,
+    RigidBody3DScheme.configure_solver, Solver.setup (which builds the device
+    scene and hands it to the integrator)."""
+    from rigid_body_2d_3d_pysph_b200.scenes import synthetic_pile
+    arrays, scheme, info = synthetic_pile(
+        bodies, seed=0, slab=(rank, world),
+        halo_cap=halo_cap if world > 1 else 0)
+    scheme.kr, scheme.kf, scheme.fric_coeff = KR, KF, MU
+    scheme.configure_solver(dt=DT, tf=1e9, pfreq=10**9, ks=args.ks,
+                            list_cap=args.list_cap,
+                            eta_uniform=info['eta_uniform'])
+    solver = scheme.solver
+    solver.setup(arrays, scheme.get_equations())
+    return arrays, info, solver
+
+
+def time_steps(run_steps, nsteps, barrier, torch, dev):
+    e0, e1 = torch.cuda.Event(enable_timing=True), \
+        torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    run_steps(nsteps)
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1)
 
 
 def main():
@@ -156,11 +204,22 @@ def main():
     ap.add_argument('--bodies', type=int, default=100000,
                     help='bodies per GPU (100 particles each)')
     ap.add_argument('--settle', type=int, default=2000)
-    ap.add_argument('--cpu-bodies', type=int, default=1000)
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help='N > 1: weak = --bodies per GPU (N piles side by '
+                    'side), strong = --bodies in total, cut into N slabs')
+    ap.add_argument('--cpu-bodies', type=int, default=10000)
     ap.add_argument('--cpu-settle', type=int, default=50)
-    ap.add_argument('--cpu-steps', type=int, default=60)
+    ap.add_argument('--cpu-steps', type=int, default=40)
+    ap.add_argument('--cpu-threads', type=int, default=0)
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-extras', action='store_true',
+                    help='skip the settled-pile, moving-wall, strong-scaling '
+                    'and DEMScheme measurements')
+    ap.add_argument('--settled-steps', type=int, default=4000)
     ap.add_argument('--ks', type=int, default=8)
+    ap.add_argument('--list-cap', type=int, default=160,
+                    help='neighbour-list entries per particle (the compacting '
+                    'pile of the later state needs more than the early one)')
     ap.add_argument('--halo-cap', type=int, default=600000)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
@@ -176,8 +235,8 @@ def main():
     import torch
     import torch.distributed as dist
     from rigid_body_2d_3d_pysph_b200 import _lib
-    from rigid_body_2d_3d_pysph_b200.device import DeviceScene
-    from rigid_body_2d_3d_pysph_b200.scenes import synthetic_pile
+    from rigid_body_2d_3d_pysph_b200.device import (BodyStateStream,
+                                                   BoundaryStream)
 
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
@@ -189,18 +248,18 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---- scene (one pile per rank: weak scaling) ---------------------------
+    # ---- scene ---------------------------------------------------------------
+    # N = 1: the whole pile on one GPU.  N > 1, weak: the scene is N such piles
+    # side by side in one walled box; strong: ONE pile of --bodies cut into N
+    # x-slabs.  Rank k owns slab k and exchanges source-particle halos with
+    # its neighbours every step.
+    strong = world > 1 and args.scaling == 'strong'
+    per_rank = args.bodies // world if strong else args.bodies
     t_build = time.perf_counter()
-    # N = 1: the whole pile on one GPU.  N > 1: weak scaling, the scene is N
-    # such piles side by side in one walled box, rank k owns x-slab k and
-    # exchanges source-particle halos with its neighbours every step.
-    arrays, scheme, info = synthetic_pile(
-        args.bodies, seed=0, slab=(rank, world),
-        halo_cap=args.halo_cap if world > 1 else 0)
+    arrays, info, solver = build_scene(args, rank, world, per_rank,
+                                       args.halo_cap, dev)
     body, wall = arrays[0], arrays[1]
-    sc = DeviceScene(arrays, ['body'], [a.name for a in arrays[1:]], dim=3,
-                     kr=KR, kf=KF, fric_coeff=MU, gy=-9.81, ks=args.ks,
-                     eta_uniform=info['eta_uniform'], device=dev)
+    sc, integ = solver.scene, solver.integrator
     t_build = time.perf_counter() - t_build
     n_rigid = sc.n_rigid
     n_static_src = info['n_wall_sources']
@@ -213,8 +272,9 @@ def main():
         if slab is not None:
             slab.gtvf_step(DT, n)
         else:
-            sc.gtvf_step(DT, n, graph=True)
+            integ.step(0., DT, n, graph=True)
 
+    note('scene built (%d particles), settling' % n_rigid)
     # ---- pre-settle, warm-up -------------------------------------------------
     run_steps(args.settle)
     run_steps(args.warmup)
@@ -222,19 +282,13 @@ def main():
     sc.check_status()
     sc.read_counters(reset=True)
 
+    note('timed region')
     # ---- timed region: K steps, device time, max over ranks -----------------
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), \
-        torch.cuda.Event(enable_timing=True)
-    barrier()
     halo0 = slab.bytes_recv if slab is not None else 0
-    e0.record()
-    run_steps(args.steps)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    ms = time_steps(run_steps, args.steps, barrier, torch, dev)
     sampler.stop_flag = True
     halo_bytes = (slab.bytes_recv - halo0) / args.steps if slab is not None \
         else 0
@@ -245,49 +299,49 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
         c = torch.tensor([cnt['gated_pairs'], cnt['active_slots'],
-                          cnt['candidates'], n_rigid], dtype=torch.float64,
-                         device=dev)
+                          cnt['candidates'], n_rigid, cnt['list_entries']],
+                         dtype=torch.float64, device=dev)
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        tot_pairs, tot_active, tot_cand, tot_rigid = (float(v) for v in c)
+        tot_pairs, tot_active, tot_cand, tot_rigid, tot_list = (
+            float(v) for v in c)
     else:
-        tot_pairs, tot_active, tot_cand, tot_rigid = (
+        tot_pairs, tot_active, tot_cand, tot_rigid, tot_list = (
             float(cnt['gated_pairs']), float(cnt['active_slots']),
-            float(cnt['candidates']), float(n_rigid))
+            float(cnt['candidates']), float(n_rigid),
+            float(cnt['list_entries']))
     sec = ms * 1e-3
     value = tot_rigid * args.steps / sec
     pairs_per_s = tot_pairs / sec
 
-    # ---- dominant kernel alone (contact), CUDA events on its stream ---------
-    # `contact_ms`: average over evaluations as they occur in the run (the
-    # neighbour lists are reused until a body has moved half the skin, so
-    # most evaluations are k_slots alone); `contact_rebuild_ms`: an
-    # evaluation that rebuilds the lists (k_neighbours + k_slots).
+    note('%.3f ms/step; kernel timings' % (ms / args.steps))
+    # ---- the dominant kernels alone, CUDA events on their stream ------------
+    # `contact_ms`: the pair kernels of one contact evaluation on REUSED lists
+    # (k_sparse_reset + k_filter + k_slots: what every step runs);
+    # `rebuild_ms`: what a list rebuild adds (cell list, k_neighbours,
+    # k_list_sort), paid when a body has moved half the skin.
+    import ctypes
     p = sc.params(DT)
-    kms, kms_rebuild = [], []
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    for it_ in range(14):
-        forced = it_ >= 10
-        sc.gtvf_kick(DT)
-        sc.gtvf_drift(DT)
-        sc.pose(_lib.POSE_POS | _lib.POSE_VEL | _lib.POSE_VEL_PREV |
-                _lib.POSE_NORMALS)
-        if forced:
-            sc.force_rebuild()
-        if slab is not None:
-            slab.exchange_halo(full=slab.lists_need_rebuild())
-        sc.cells_build()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    t_reb, t_con = [], []
+    for it_ in range(6):
+        sc.force_rebuild()
         ev[0].record()
-        sc.contact(DT)
+        sc.cells_build()
+        _lib.check(sc.lib.rbx_contact_neighbours(
+            ctypes.byref(sc.scene), ctypes.byref(sc._cells), ctypes.byref(p),
+            sc.stream))
         ev[1].record()
-        sc.reduce_bodies()
-        sc.gtvf_kick(DT)
-        sc.pose(_lib.POSE_VEL)
+        _lib.check(sc.lib.rbx_contact_slots(
+            ctypes.byref(sc.scene), ctypes.byref(sc._cells), ctypes.byref(p),
+            None, sc.stream))
+        ev[2].record()
         torch.cuda.synchronize(dev)
-        (kms_rebuild if forced else kms).append(ev[0].elapsed_time(ev[1]))
-    if not kms:
-        kms = list(kms_rebuild)
-    contact_rebuild_ms = float(np.mean(kms_rebuild[1:]))
-    contact_ms = float(np.mean(kms[1:]))
+        t_reb.append(ev[0].elapsed_time(ev[1]))
+        t_con.append(ev[1].elapsed_time(ev[2]))
+    rebuild_ms = float(np.mean(t_reb[2:]))
+    contact_ms = float(np.mean(t_con[2:]))
+    list_entries = float(sc.T['nbr_cnt'].bitwise_and(0x3fffffff).sum().item())
+    rebuilds_per_step = tot_list / world / max(list_entries, 1.) / args.steps
     active_per_step = tot_active / args.steps / world
     step_b, contact_b = algorithmic_bytes(n_rigid, n_static_src,
                                           active_per_step, sc.n_bodies)
@@ -295,144 +349,190 @@ def main():
     traffic = None
     limiter = None
     try:
-        with open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')) as f:
+        with open(os.path.join(ROOT, 'profiles', 'r02_traffic.json')) as f:
             tr = json.load(f)
-        if tr['config']['bodies'] == args.bodies:
-            # DRAM bytes of an average evaluation: k_slots every time, the
-            # rebuild kernels on the share of evaluations that rebuild
-            share = 0. if contact_rebuild_ms <= contact_ms else \
-                (contact_ms - min(kms[1:])) / max(
-                    contact_rebuild_ms - min(kms[1:]), 1e-9)
-            traffic = tr['contact_dram_bytes_per_evaluation'] + \
-                share * tr['contact_dram_bytes_per_rebuild']
+        if tr['config']['bodies'] == per_rank:
+            traffic = tr['contact_dram_bytes_per_evaluation']
             limiter = '; '.join(
-                '%s: %.0f %% FP64 pipe, %.0f %% issue active, %.1f of 32 '
-                'lanes, %d registers' % (
-                    n.split(' ')[0], k['fp64_pipe_pct'],
-                    k['issue_active_pct'], k['threads_per_inst'],
-                    k['registers'])
+                '%s: %.2f ms, %.0f %% issue active, %.1f of 32 lanes, %d '
+                'registers, FP64 pipe %.0f %%' % (
+                    n, k['ms'], k['issue_active_pct'], k['threads_per_inst'],
+                    k['registers'], k['fp64_pipe_pct'])
                 for n, k in tr['kernels'].items())
     except Exception:
         pass
     roof = {'bound': 'hbm',
-            'kernel': 'contact evaluation (rbx_contact_mofidi): k_slots, plus '
-            'k_neighbours + k_list_sort on the steps that rebuild the '
-            'neighbour lists',
+            'kernel': 'contact evaluation on reused neighbour lists '
+            '(rbx_contact_slots: k_sparse_reset, k_filter = FP32 first pass '
+            'over every list entry, k_slots = exact FP64 pass over what it '
+            'could not exclude)',
             'achieved': contact_b / (contact_ms * 1e-3) / 1e9, 'peak': peak,
             'unit': 'GB/s', 'peak_source': peak_src, 'traffic': traffic,
-            'traffic_source': 'profiles/r01_traffic.json (ncu dram__bytes '
-            'read+write per launch, rebuild kernels weighted by the share of '
-            'evaluations that rebuild)' if traffic else None,
-            'secondary_limiter': ('FP64 issue and latency, not HBM (ncu, '
-                                  'profiles/r01_traffic.json): ' + limiter)
+            'traffic_source': 'profiles/r02_traffic.json (ncu dram__bytes '
+            'read+write of k_filter + k_slots, one evaluation)'
+            if traffic else None,
+            'secondary_limiter': ('instruction issue (FP32 pair math over '
+                                  '%.3g list entries per step), not HBM; '
+                                  'ncu, profiles/r02_traffic.json: ' %
+                                  list_entries + limiter)
             if limiter else None,
             'ms_per_launch': contact_ms,
-            'ms_per_launch_with_list_rebuild': contact_rebuild_ms,
+            'list_rebuild_ms': rebuild_ms,
+            'list_rebuilds_per_step': rebuilds_per_step,
+            'ms_per_evaluation_average': contact_ms +
+            rebuilds_per_step * rebuild_ms,
             'algorithmic_bytes_per_launch': contact_b}
     roof['frac'] = roof['achieved'] / peak
-    step_roof = {'bound': 'hbm', 'achieved': step_b * world /
-                 (sec / args.steps) / 1e9 / world, 'peak': peak,
+    step_roof = {'bound': 'hbm', 'achieved': step_b /
+                 (sec / args.steps) / 1e9, 'peak': peak,
                  'unit': 'GB/s', 'algorithmic_bytes_per_step': step_b}
     step_roof['frac'] = step_roof['achieved'] / peak
 
-    # ---- e2e through the host-facing API: host-driven boundary in, body
-    #      state out, every step ----------------------------------------------
-    wall_o = sc.p_off['wall']
+    note('e2e')
+    # ---- e2e through the public API: host-driven boundary in, body state out,
+    #      every step ----------------------------------------------------------
+    # BoundaryStream.submit / apply = pinned host -> staging -> scene (the
+    # lists are rebuilt only if the wall really moved more than half the
+    # skin), Integrator.step = one GTVF step, BodyStateStream.snapshot / wait
+    # = per-body results -> pinned host.  Every step consumes its own upload
+    # and every step's result is on the host inside the timed region.
     wall_n = wall.get_number_of_particles()
-    names_in = ['x', 'y', 'z', 'u', 'v', 'w']
-    host_in = dict((n, torch.from_numpy(
-        np.ascontiguousarray(wall.properties[n])).pin_memory())
-        for n in names_in)
-    names_out = ['xcm', 'vcm', 'omega', 'R', 'force', 'torque']
-    host_out = dict((n, torch.empty_like(sc.B[n], device='cpu').pin_memory())
-                    for n in names_out)
-    h2d = sum(t.numel() * 8 for t in host_in.values())
-    d2h = sum(t.numel() * 8 for t in host_out.values())
+    names_in = ('x', 'y', 'z', 'u', 'v', 'w')
+    feeder = BoundaryStream(sc, 'wall', names_in)
+    reader = BodyStateStream(sc)
+    base = dict((n, torch.from_numpy(
+        np.ascontiguousarray(wall.properties[n]))) for n in names_in)
+    host_in = [dict((n, base[n].clone().pin_memory()) for n in names_in)
+               for _ in range(2)]
+    h2d, d2h = feeder.bytes_per_submit, reader.bytes_per_snapshot
     e2e_steps = max(3, min(args.steps, 50))
+    amp, freq = 0.2 * info['dx'], 50.          # the moving wall: a shaker
 
-    # Double-buffered, as a host application that drives the boundary would
-    # do it: a copy stream uploads the wall state of step k + 1 into a device
-    # staging buffer and downloads the body state of step k - 1 from a device
-    # snapshot while step k computes.  Every step still consumes its own
-    # upload and every step's result reaches pinned host memory inside the
-    # timed region.
-    cur = torch.cuda.current_stream(dev)
-    copy_s = torch.cuda.Stream(dev)
-    stage = [dict((n, torch.empty(wall_n, dtype=torch.float64, device=dev))
-                  for n in names_in) for _ in range(2)]
-    snap = [dict((n, torch.empty_like(sc.B[n])) for n in names_out)
-            for _ in range(2)]
-    host_res = [host_out, dict((n, torch.empty_like(host_out[n]).pin_memory())
-                               for n in names_out)]
-    ev_up = [torch.cuda.Event() for _ in range(2)]
-    ev_used = [torch.cuda.Event() for _ in range(2)]
-    ev_snap = [torch.cuda.Event() for _ in range(2)]
-    ev_out = [torch.cuda.Event() for _ in range(2)]
-    for e in ev_used + ev_out:
-        e.record(cur)
+    def wall_state(k, moving):
+        h = host_in[k & 1]
+        if moving:
+            feeder.ev_up[k & 1].synchronize()   # its last upload has left
+            ph = 2. * np.pi * freq * DT * k
+            h['x'].copy_(base['x'] + amp * np.sin(ph))
+            h['u'].fill_(amp * 2. * np.pi * freq * np.cos(ph))
+        return h
 
-    def upload(k):
-        with torch.cuda.stream(copy_s):
-            copy_s.wait_event(ev_used[k & 1])     # staging buffer is free
-            for n in names_in:
-                stage[k & 1][n].copy_(host_in[n], non_blocking=True)
-            ev_up[k & 1].record(copy_s)
-
-    def step(k):
-        cur.wait_event(ev_up[k & 1])
-        for n in names_in:
-            sc.P[n][wall_o:wall_o + wall_n].copy_(stage[k & 1][n])
-        ev_used[k & 1].record(cur)
-        if slab is not None:
-            slab.gtvf_step(DT, 1)
-        else:
-            sc._gtvf_step_call(p)
-        cur.wait_event(ev_out[k & 1])             # snapshot buffer is free
-        for n in names_out:
-            snap[k & 1][n].copy_(sc.B[n])
-        ev_snap[k & 1].record(cur)
-        with torch.cuda.stream(copy_s):
-            copy_s.wait_event(ev_snap[k & 1])
-            for n in names_out:
-                host_res[k & 1][n].copy_(snap[k & 1][n], non_blocking=True)
-            ev_out[k & 1].record(copy_s)
-
-    def run_e2e(nsteps):
-        upload(0)
+    def run_e2e(nsteps, moving):
+        feeder.submit(wall_state(0, moving))
+        last = -1
         for k in range(nsteps):
             if k + 1 < nsteps:
-                upload(k + 1)
-            step(k)
-            if k > 0:
-                ev_out[(k - 1) & 1].synchronize()   # result of step k - 1 is on the host
-        ev_out[(nsteps - 1) & 1].synchronize()
-        cur.synchronize()
+                feeder.submit(wall_state(k + 1, moving))
+            feeder.apply()
+            if slab is not None:
+                slab.gtvf_step(DT, 1)
+            else:
+                integ.step(k * DT, DT, 1)
+            j = reader.snapshot()
+            if last >= 0:
+                reader.wait(last)        # result of step k - 1 is on the host
+            last = j
+        reader.wait(last)
+        torch.cuda.current_stream(dev).synchronize()
 
-    run_e2e(3)
-    barrier()
-    t0 = time.perf_counter()
-    run_e2e(e2e_steps)
-    barrier()
-    e2e_sec = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_sec], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_sec = float(t.item())
-    e2e = {'value': tot_rigid * e2e_steps / e2e_sec, 'unit': UNIT,
+    def time_e2e(moving):
+        run_e2e(3, moving)
+        barrier()
+        t0 = time.perf_counter()
+        run_e2e(e2e_steps, moving)
+        barrier()
+        dt_ = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt_], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt_ = float(t.item())
+        return tot_rigid * e2e_steps / dt_
+
+    e2e = {'value': time_e2e(False), 'unit': UNIT,
            'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
            'steps': e2e_steps,
-           'what': 'per step: wall x,y,z,u,v,w pinned host->device '
-           '(host-driven boundary, as post_step moves it), one GTVF step '
-           'through rbx_gtvf_step, per-body xcm,vcm,omega,R,force,torque '
-           'device->pinned host; copies double-buffered on a second stream '
-           '(upload of step k+1 and download of step k-1 overlap step k), '
-           'wall clock over all steps with every result on the host'}
+           'what': 'per step, through the public API: wall x,y,z,u,v,w from '
+           'pinned host memory (BoundaryStream.submit/apply -> '
+           'DeviceScene.static_update), one GTVF step (Integrator.step; '
+           'slabs: SlabScene.gtvf_step), per-body xcm,vcm,omega,R,force,'
+           'torque to pinned host memory (BodyStateStream); copies run on '
+           'a second stream one step ahead / behind; wall clock over all '
+           'steps with every result on the host.  The wall data are the '
+           'same every step (a static boundary, uploaded all the same); '
+           'moving_wall has one that moves'}
     sc.check_status()
+    extras = {}
+    if not args.no_extras:
+        note('e2e with a moving wall')
+        e2e['moving_wall'] = {
+            'value': time_e2e(True), 'unit': UNIT,
+            'what': 'the same loop with the whole wall shaken along x '
+            '(%.3g m amplitude, %.0f Hz): the lists are rebuilt whenever '
+            'it has moved half the skin' % (amp, freq)}
+        run_e2e(1, False)                  # put the wall back
+        sc.check_status()
 
+    note('e2e done; extras')
+    # ---- a settled pile (N = 1): the same scene much later --------------------
+    if world == 1 and not args.no_extras and args.settled_steps > 0:
+        run_steps(args.settled_steps)
+        sc.read_counters(reset=True)
+        ms2 = time_steps(run_steps, args.steps, barrier, torch, dev)
+        c2 = sc.read_counters(reset=True)
+        sc.check_status()
+        extras['settled_pile'] = {
+            'what': 'the same scene after %d more steps (t = %.2f s): the '
+            'pile is compacting, ten times as many slots are in contact and '
+            'the exact FP64 pass, not the FP32 first pass, is the cost' % (
+                args.settled_steps, DT * (args.settle + args.settled_steps)),
+            'ms_per_step': ms2 / args.steps,
+            'value': n_rigid * args.steps / (ms2 * 1e-3), 'unit': UNIT,
+            'contact_pairs_per_step': c2['gated_pairs'] / args.steps,
+            'active_slots_per_step': c2['active_slots'] / args.steps,
+            'list_rebuilds_per_step': c2['list_entries'] / max(
+                float(sc.T['nbr_cnt'].bitwise_and(0x3fffffff).sum().item()),
+                1.) / args.steps}
+
+    # ---- strong scaling (N > 1): ONE pile of --bodies cut into N slabs -------
+    if world > 1 and not strong and not args.no_extras:
+        del feeder, reader, slab, sc, integ, solver
+        torch.cuda.empty_cache()
+        from rigid_body_2d_3d_pysph_b200.parallel import SlabScene
+        arr2, info2, solver2 = build_scene(args, rank, world,
+                                           args.bodies // world,
+                                           args.halo_cap, dev)
+        slab2 = SlabScene(solver2.scene, rank, world)
+        slab2.gtvf_step(DT, args.settle + args.warmup)
+        barrier()
+        ms3 = time_steps(lambda n: slab2.gtvf_step(DT, n), args.steps,
+                         barrier, torch, dev)
+        t = torch.tensor([ms3], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        solver2.scene.check_status()
+        n_tot = float(info2['n_body_particles']) * world
+        extras['strong_scaling'] = {
+            'what': 'ONE pile of %d bodies (%d particles) cut into %d '
+            'x-slabs (bench.py --scaling strong runs only this)' % (
+                (args.bodies // world) * world, int(n_tot), world),
+            'ms_per_step': float(t.item()) / args.steps,
+            'value': n_tot * args.steps / (float(t.item()) * 1e-3),
+            'unit': UNIT}
+
+    note('dem')
+    # ---- DEMScheme path (N = 1): spheres on a vibrating floor ----------------
+    if world == 1 and not args.no_extras:
+        try:
+            extras['dem_scheme'] = bench_dem(torch, dev)
+        except Exception as exc:      # an extra: never takes the line down
+            extras['dem_scheme'] = {'error': repr(exc)}
+
+    note('cpu baseline')
     # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle import rbo
+        from rigid_body_2d_3d_pysph_b200.scenes import synthetic_pile
+        threads = rbo.set_num_threads(args.cpu_threads or host_cores())
         (cb, cw), _, cinfo = synthetic_pile(args.cpu_bodies, seed=0)
         rbo.add_sparse_history(cb, 4)
         cp = rbo.make_params(3, DT, KR, KF, MU, 0., -9.81, 0.,
@@ -443,31 +543,31 @@ def main():
         rbo.gtvf_step([cb, cw], ['body'], cp, ks=4, nsteps=args.cpu_steps)
         cdt = time.perf_counter() - t0
         cpu = {'value': cinfo['n_body_particles'] * args.cpu_steps / cdt,
-               'unit': UNIT, 'cores': rbo.num_threads(), 'kind': 'port',
+               'unit': UNIT, 'cores': threads, 'kind': 'port',
                'sample': '%d-body / %d-particle pile, %d settle + %d timed '
-               'steps, C/OpenMP restatement (oracle/rbo.c)' % (
+               'steps, C/OpenMP restatement (oracle/rbo.c, gcc -O3)' % (
                    args.cpu_bodies, cinfo['n_body_particles'],
                    min(args.settle, args.cpu_settle), args.cpu_steps)}
 
     if rank == 0:
-        launches_per_step = 18   # bodies, pose, 8 cell-list kernels,
-        #                          k_neighbours, k_list_sort, list commit + clear,
-        #                          k_slots, bodies (reduce), bodies (kick), pose (memsets not
-        #                          counted; the cell-list kernels and
-        #                          k_neighbours return at once on steps
-        #                          that reuse the neighbour lists)
+        # k_bodies, k_pose, 8 cell-list kernels, k_neighbours, k_pos32,
+        # k_list_sort, k_list_commit, k_static_commit, k_list_clear,
+        # k_sparse_reset, k_filter, k_slots, k_reduce, k_bodies (memsets not
+        # counted; the cell-list and list kernels return at once on the
+        # steps that reuse the neighbour lists)
+        launches_per_step = 21
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT,
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms / args.steps, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
-            'data': 'synthetic',
+            'scaling': 'strong' if strong else 'weak', 'vs_baseline': None,
+            'dtype': 'f64', 'data': 'synthetic',
             'config': {
                 'workload': 'synthetic 3D pile, %d blocks of 5x5x4 / %d '
                 'particles per GPU + %d wall particles (BASELINE.json '
                 'config 5), pre-settled %d steps, dt=1e-4' % (
-                    args.bodies, n_rigid, wall_n, args.settle),
-                'bodies_per_gpu': args.bodies,
+                    per_rank, n_rigid, wall_n, args.settle),
+                'bodies_per_gpu': per_rank,
                 'particles_per_gpu': n_rigid,
                 'parallelism': ('%d x-slabs of one scene, bodies owned per '
                                 'slab, source-particle halo exchange (NCCL '
@@ -476,7 +576,10 @@ def main():
                 'halo_bytes_per_rank_per_step': halo_bytes,
                 'l2': 'working set (%.1f GB) far larger than the 126 MB L2; '
                 'no flush needed' % (step_b / 1e9),
-                'stepper': 'GTVF', 'ks': args.ks, 'graph': world == 1},
+                'stepper': 'GTVF', 'ks': args.ks,
+                'skin_factor': solver.skin_factor if world == 1 or strong
+                else 0.075,
+                'graph': world == 1},
             'contact_pairs_per_s': pairs_per_s,
             'contact_pairs_per_step': tot_pairs / args.steps,
             'active_slots_per_step': tot_active / args.steps,
@@ -487,9 +590,77 @@ def main():
             'clocks': sampler.summary(),
             'scene_build_s': t_build,
         }
+        line.update(extras)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_dem(torch, dev, n_side=64, steps=200):
+    """DEMScheme (dem.py: LVCDisplacement + DEMStep): a
+    packed block of n_side^3 spheres, slightly overlapping, on a floor of
+    spheres.  No script of the reference instantiates the scheme; the
+    constants it needs are those of the parity fixture (tests/golden/dem2d)."""
+    from rigid_body_2d_3d_pysph_b200.dem import DEMScheme
+    from rigid_body_2d_3d_pysph_b200.compat.particle_array import \
+        get_particle_array
+    rad = 0.005
+    i, j, k = np.meshgrid(np.arange(n_side), np.arange(n_side),
+                          np.arange(n_side), indexing='ij')
+    rng = np.random.default_rng(1)
+    n = i.size
+    x = i.ravel() * 1.98 * rad + rng.uniform(-0.02, 0.02, n) * rad
+    y = j.ravel() * 1.97 * rad + 0.99 * rad + rng.uniform(-0.02, 0.02, n) * rad
+    z = k.ravel() * 1.98 * rad + rng.uniform(-0.02, 0.02, n) * rad
+    rho = 2500.
+    m = rho * 4. / 3. * np.pi * rad**3
+    sand = get_particle_array(name='sand', x=x, y=y, z=z, h=1.2 * rad, m=m,
+                              rho=rho, rad_s=rad,
+                              u=rng.uniform(-0.05, 0.05, n),
+                              v=rng.uniform(-0.05, 0.05, n),
+                              w=rng.uniform(-0.05, 0.05, n))
+    sand.add_property('dem_id', type='int', data=0)
+    sand.add_property('moi', data=0.4 * m * rad**2)
+    fi, fk = np.meshgrid(np.arange(-2, n_side + 2), np.arange(-2, n_side + 2),
+                         indexing='ij')
+    floor = get_particle_array(name='floor', x=fi.ravel() * 2. * rad,
+                               y=np.zeros(fi.size) - rad,
+                               z=fk.ravel() * 2. * rad, h=1.2 * rad, m=m,
+                               rho=rho, rad_s=rad)
+    floor.add_property('dem_id', type='int', data=1)
+    for pa in (sand, floor):
+        for p in ('wx', 'wy', 'wz'):
+            pa.add_property(p)
+    sand.add_constant('max_tng_contacts_limit', 16)
+    sand.add_constant('kn', [1e5, 2e5])
+    sand.add_constant('kt', [2. / 7. * 1e5, 2. / 7. * 2e5])
+    sand.add_constant('alpha', [40., 60.])
+    sand.add_constant('mu', [0.5, 0.3])
+    s = DEMScheme(['sand'], ['floor'], dim=3, gy=-9.81)
+    dt = 2e-6
+    s.configure_solver(dt=dt, tf=1e9, pfreq=10**9)
+    s.setup_properties([sand, floor])
+    solver = s.get_solver()
+    solver.setup([sand, floor], s.get_equations(), kernel=solver.kernel)
+    integ = solver.integrator
+    integ.step(0., dt, 20)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), \
+        torch.cuda.Event(enable_timing=True)
+    e0.record()
+    integ.step(0., dt, steps)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    solver.scene.check_status()
+    solver.scene.sync_to_host()
+    return {'what': 'DEMScheme (LVCDisplacement contact with per-pair '
+            'tangential history + DEMStep): %d spheres in a packed block on '
+            'a floor of %d, dt = %g' % (n, floor.get_number_of_particles(),
+                                        dt),
+            'ms_per_step': ms, 'value': n / (ms * 1e-3),
+            'unit': 'particle-updates/s',
+            'tangential_contacts': int(sand.total_tng_contacts.sum())}
 
 
 if __name__ == '__main__':

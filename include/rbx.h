@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RBX_VERSION 400 /* 0.4.0 */
+#define RBX_VERSION 402 /* 0.4.2 */
 
 typedef enum {
   RBX_OK = 0,
@@ -211,6 +211,11 @@ typedef struct {
   const float *aux32;
   double h_uniform;
   double gravity[3];  /* = RbxParams.gx, gy, gz (force of an untagged body) */
+  /* [3 (n_total - n_rigid)] x, y, z of the static particles (walls, halo) when
+   * the neighbour lists were last built, or NULL.  rbx_static_update and
+   * rbx_halo_unpack raise `rebuild` when one of them has moved more than
+   * skin / 2 since -- the rule the drift kernel applies to the bodies.       */
+  double *static_ref;
 } RbxScene;
 
 typedef struct {
@@ -367,6 +372,16 @@ int rbx_pose_particles(const RbxScene *scene, int flags, void *stream);
 int rbx_pos32_refresh(const RbxScene *scene, int32_t first, int32_t n,
                       void *stream);
 
+/* Host-driven boundaries (an Application's post_step moving a wall,
+ * stack_of_cylinders.py:438-445): new state of the static particles
+ * [first, first + n) from device buffers (any of x..w may be NULL = keep),
+ * pos32 refreshed, `rebuild` raised if a particle is now further than
+ * skin / 2 from where it was when the lists were built (static_ref).        */
+int rbx_static_update(const RbxScene *scene, int32_t first, int32_t n,
+                      const double *x, const double *y, const double *z,
+                      const double *u, const double *v, const double *w,
+                      double skin, void *stream);
+
 /* Multi-GPU halo payload (no counterpart in the reference, which is single
  * process): rows of 8 doubles {x, y, z, u, v, w, h, dem_id}.  pack gathers
  * the particles index[0..n) into rows[n][8]; unpack writes rows[n][8] into
@@ -374,7 +389,7 @@ int rbx_pos32_refresh(const RbxScene *scene, int32_t first, int32_t n,
 int rbx_halo_pack(const RbxScene *scene, const int64_t *index, int32_t n,
                   double *rows, void *stream);
 int rbx_halo_unpack(const RbxScene *scene, int32_t first, int32_t n,
-                    const double *rows, void *stream);
+                    const double *rows, double skin, void *stream);
 
 /* RK2RigidBody3DStep (rigid_body_3d.py:406-575): stage 0 = py_initialize
  * (fix_q7 != 0 saves ang_mom0 of every body), 1 and 2 =

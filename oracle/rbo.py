@@ -219,6 +219,12 @@ def num_threads():
     return lib().rbo_num_threads()
 
 
+def set_num_threads(n):
+    """OpenMP threads of the following calls (n <= 0: leave as is)."""
+    lib().rbo_set_num_threads(int(n))
+    return num_threads()
+
+
 def dem_step(arrays, granular_names, params, nsteps=1):
     """GTVF step of the DEMScheme path (LVCDisplacement + DEMStep)."""
     L = lib()

@@ -65,7 +65,8 @@ class RbxScene(ctypes.Structure):
                [(n, c_vp) for n in _SCENE_PTRS] + [('origin', c_f64 * 3)] + \
                [(n, c_vp) for n in ('alist_out', 'alist_prev', 'acount_out',
                                     'acount_prev', 'body_tag', 'aux32')] + \
-               [('h_uniform', c_f64), ('gravity', c_f64 * 3)]
+               [('h_uniform', c_f64), ('gravity', c_f64 * 3),
+                ('static_ref', c_vp)]
 
 
 _DEM_PTRS = ['x', 'y', 'z', 'u', 'v', 'w', 'wx', 'wy', 'wz', 'h', 'm', 'rad_s',
@@ -107,7 +108,7 @@ SYMBOLS = ['rbx_version', 'rbx_strerror', 'rbx_sizeof',
            'rbx_contact_mofidi', 'rbx_contact_neighbours',
            'rbx_contact_slots', 'rbx_contact_canelas', 'rbx_reduce_bodies', 'rbx_gtvf_kick',
            'rbx_gtvf_drift', 'rbx_pose_particles', 'rbx_pos32_refresh',
-           'rbx_halo_pack',
+           'rbx_halo_pack', 'rbx_static_update',
            'rbx_halo_unpack', 'rbx_rk2_stage',
            'rbx_gtvf_step', 'rbx_contact_lvc', 'rbx_dem_step',
            'rbx_boundary_identify']
@@ -159,7 +160,10 @@ def load():
     L.rbx_pose_particles.argtypes = [P(RbxScene), ctypes.c_int, c_vp]
     L.rbx_pos32_refresh.argtypes = [P(RbxScene), c_i32, c_i32, c_vp]
     L.rbx_halo_pack.argtypes = [P(RbxScene), c_vp, c_i32, c_vp, c_vp]
-    L.rbx_halo_unpack.argtypes = [P(RbxScene), c_i32, c_i32, c_vp, c_vp]
+    L.rbx_halo_unpack.argtypes = [P(RbxScene), c_i32, c_i32, c_vp, c_f64,
+                                  c_vp]
+    L.rbx_static_update.argtypes = [P(RbxScene), c_i32, c_i32, c_vp, c_vp,
+                                    c_vp, c_vp, c_vp, c_vp, c_f64, c_vp]
     L.rbx_rk2_stage.argtypes = [P(RbxScene), ctypes.c_int, c_f64,
                                 ctypes.c_int, c_f64, c_vp]
     L.rbx_gtvf_step.argtypes = [P(RbxScene), P(RbxPoints), P(RbxCells),

@@ -263,7 +263,17 @@ __global__ void k_halo_pack(RbxScene S, const int64_t *index, int n, double *row
   const double *col[7] = {S.x, S.y, S.z, S.u, S.v, S.w, S.h};
   rows[k] = c < 7 ? col[c][q] : (double)S.dem_id[q];
 }
-__global__ void k_halo_unpack(RbxScene S, int first, int n, const double *rows) {
+// a static particle (wall, halo) that is now further than skin / 2 from where
+// it was when the neighbour lists were built asks for a rebuild
+__device__ __forceinline__ void check_static(const RbxScene &S, int q, double x, double y,
+                                             double z, double skin) {
+  if (!S.static_ref || !S.rebuild) return;
+  const double *r = S.static_ref + 3 * (size_t)(q - S.n_rigid);
+  const double dx = x - r[0], dy = y - r[1], dz = z - r[2];
+  if (!(dx * dx + dy * dy + dz * dz <= 0.25 * skin * skin)) atomicOr(S.rebuild, 1u);
+}
+
+__global__ void k_halo_unpack(RbxScene S, int first, int n, const double *rows, double skin) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n * 8) return;
   const int c = k & 7;
@@ -271,11 +281,35 @@ __global__ void k_halo_unpack(RbxScene S, int first, int n, const double *rows) 
   double *col[7] = {S.x, S.y, S.z, S.u, S.v, S.w, const_cast<double *>(S.h)};
   if (c < 7) col[c][q] = rows[k];
   else const_cast<int32_t *>(S.dem_id)[q] = (int32_t)rows[k];
-  if (c == 0 && S.pos32) {
+  if (c == 0) {
     const double *r = rows + (size_t)(k >> 3) * 8;
-    reinterpret_cast<float4 *>(S.pos32)[q] =
-        make_float4((float)(r[0] - S.origin[0]), (float)(r[1] - S.origin[1]),
-                    (float)(r[2] - S.origin[2]), (float)r[6]);
+    if (S.pos32)
+      reinterpret_cast<float4 *>(S.pos32)[q] =
+          make_float4((float)(r[0] - S.origin[0]), (float)(r[1] - S.origin[1]),
+                      (float)(r[2] - S.origin[2]), (float)r[6]);
+    check_static(S, q, r[0], r[1], r[2], skin);
+  }
+}
+
+__global__ void k_static_update(RbxScene S, int first, int n, const double *x, const double *y,
+                                const double *z, const double *u, const double *v,
+                                const double *w, double skin) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int q = first + k;
+  if (x) S.x[q] = x[k];
+  if (y) S.y[q] = y[k];
+  if (z) S.z[q] = z[k];
+  if (u) S.u[q] = u[k];
+  if (v) S.v[q] = v[k];
+  if (w) S.w[q] = w[k];
+  if (x || y || z) {
+    const double xn = S.x[q], yn = S.y[q], zn = S.z[q];
+    if (S.pos32)
+      reinterpret_cast<float4 *>(S.pos32)[q] =
+          make_float4((float)(xn - S.origin[0]), (float)(yn - S.origin[1]),
+                      (float)(zn - S.origin[2]), (float)S.h[q]);
+    check_static(S, q, xn, yn, zn, skin);
   }
 }
 
@@ -323,12 +357,25 @@ extern "C" int rbx_halo_pack(const RbxScene *scene, const int64_t *index, int32_
   return RBX_OK;
 }
 
+extern "C" int rbx_static_update(const RbxScene *scene, int32_t first, int32_t n,
+                                 const double *x, const double *y, const double *z,
+                                 const double *u, const double *v, const double *w,
+                                 double skin, void *stream) {
+  if (!scene || n < 0 || first < scene->n_rigid || (long long)first + n > scene->n_total)
+    return RBX_ERR_INVALID;
+  if (n == 0) return RBX_OK;
+  k_static_update<<<rbx_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(*scene, first, n, x, y, z,
+                                                                        u, v, w, skin);
+  RBX_CHECK_LAUNCH();
+  return RBX_OK;
+}
+
 extern "C" int rbx_halo_unpack(const RbxScene *scene, int32_t first, int32_t n,
-                               const double *rows, void *stream) {
+                               const double *rows, double skin, void *stream) {
   if (!scene || n < 0 || first < 0 || (long long)first + n > scene->n_total ||
       (n > 0 && !rows)) return RBX_ERR_INVALID;
   if (n == 0) return RBX_OK;
-  k_halo_unpack<<<rbx_blocks((long long)n * 8, 256), 256, 0, (cudaStream_t)stream>>>(*scene, first, n, rows);
+  k_halo_unpack<<<rbx_blocks((long long)n * 8, 256), 256, 0, (cudaStream_t)stream>>>(*scene, first, n, rows, skin);
   RBX_CHECK_LAUNCH();
   return RBX_OK;
 }

@@ -446,6 +446,18 @@ __global__ void k_list_commit(RbxScene S) {
   for (int k = 0; k < 9; k++) S.R_ref[9 * b + k] = S.R[9 * b + k];
 }
 
+// ... and where every static particle (walls, halo) was
+__global__ void k_static_commit(RbxScene S) {
+  if (!S.rebuild || *S.rebuild == 0u || !S.static_ref) return;
+  const int n = S.n_total - S.n_rigid;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const int q = S.n_rigid + k;
+    S.static_ref[3 * (size_t)k] = S.x[q];
+    S.static_ref[3 * (size_t)k + 1] = S.y[q];
+    S.static_ref[3 * (size_t)k + 2] = S.z[q];
+  }
+}
+
 __global__ void k_list_clear(RbxScene S, double skin) {
   if (S.counters) S.counters[7] = 0ull;      // chunk dispenser of k_neighbours
   // skin == 0: no reuse, the flag stays up and every evaluation rebuilds
@@ -794,7 +806,7 @@ park_overflow(double (*ovf)[kFields], int nk, double ax, double ay, double az, d
 template <int DIM, bool UNIFORM_H, bool COMPACT>
 __global__ void __launch_bounds__(kSlotsCta, RBX_SLOTS_MINB)
 k_slots(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
-        const __grid_constant__ RbxDiag D, double h_uniform) {
+        const __grid_constant__ RbxDiag D, double h_uniform, int dense_thr) {
   // parked slots: [slot][field][thread] -> conflict-free.  Field 7 packs
   // (closest source, some in-range source of the body) as two ints.
   __shared__ double acc[kAcc][kFields][kSlotsCta];
@@ -810,6 +822,15 @@ k_slots(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
   // multiple of the 8 warps of a sort window would give a CTA the same length
   // class every time).  A finished warp takes its next block at once instead
   // of waiting for a CTA launch.
+  // dense_thr > 0 (two-precision evaluation): the FP32 pass left
+  // counters[6] particles.  While they are few the compact list is walked;
+  // once a good part of the scene is in contact (a settled pile) the list is
+  // scattered all over the work items and the pass over EVERY particle in
+  // work-item order -- coalesced list rows, warps of equal list length --
+  // is the faster one.  Both launches are issued, one of them returns here;
+  // the results are the same either way (a run the first pass excluded adds
+  // exactly nothing).
+  if (dense_thr > 0 && (((int)S.counters[6] > dense_thr) == COMPACT)) return;
   const int nwork = COMPACT ? (int)S.counters[6] : S.n_rigid;
   const int nitems = (nwork + kSlotsCta - 1) / kSlotsCta;
   // particle and list length of the work item after this one: loaded a whole
@@ -1045,7 +1066,8 @@ k_slots(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
     }
     if (lane == 0 && na) atomicAdd(&S.counters[1], (unsigned long long)na);
     // (COMPACT: the FP32 pass has counted the pairs of every run)
-    if (!COMPACT && lane == 0 && np_) atomicAdd(&S.counters[0], (unsigned long long)np_);
+    if (!COMPACT && dense_thr == 0 && lane == 0 && np_)
+      atomicAdd(&S.counters[0], (unsigned long long)np_);
   }
 }
 
@@ -1313,6 +1335,10 @@ extern "C" int rbx_contact_neighbours(const RbxScene *scene, const RbxCells *cel
   k_list_sort<<<rbx_blocks(scene->n_rigid, kSortW), kSortW, 0, st>>>(*scene);
   if (scene->rebuild)
     k_list_commit<<<rbx_blocks(scene->n_bodies, 256), 256, 0, st>>>(*scene);
+  if (scene->rebuild && scene->static_ref && scene->n_total > scene->n_rigid) {
+    const int nbs = rbx_blocks(scene->n_total - scene->n_rigid, 256), caps = rbx_sm_count() * 8;
+    k_static_commit<<<nbs < caps ? nbs : caps, 256, 0, st>>>(*scene);
+  }
   k_list_clear<<<1, 1, 0, st>>>(*scene, params->skin);
   RBX_CHECK_LAUNCH();
   return RBX_OK;
@@ -1368,19 +1394,32 @@ extern "C" int rbx_contact_slots(const RbxScene *scene, const RbxCells *cells,
       if (uni) k_filter<2, true><<<nf, 32, 0, st>>>(*scene, *params, hu);
       else k_filter<2, false><<<nf, 32, 0, st>>>(*scene, *params, 0.f);
     }
+    // exact pass: over the compact list, or over every particle when the
+    // list has grown past 1/8 of them (see k_slots)
+    const int thr = scene->n_rigid / 8 > 0 ? scene->n_rigid / 8 : 1;
     if (scene->dim == 3) {
-      if (uni) k_slots<3, true, true><<<ng, kSlotsCta, 0, st>>>(*scene, *params, d, params->h_uniform);
-      else k_slots<3, false, true><<<ng, kSlotsCta, 0, st>>>(*scene, *params, d, 0.);
+      if (uni) {
+        k_slots<3, true, true><<<ng, kSlotsCta, 0, st>>>(*scene, *params, d, params->h_uniform, thr);
+        k_slots<3, true, false><<<ng, kSlotsCta, 0, st>>>(*scene, *params, d, params->h_uniform, thr);
+      } else {
+        k_slots<3, false, true><<<ng, kSlotsCta, 0, st>>>(*scene, *params, d, 0., thr);
+        k_slots<3, false, false><<<ng, kSlotsCta, 0, st>>>(*scene, *params, d, 0., thr);
+      }
     } else {
-      if (uni) k_slots<2, true, true><<<ng, kSlotsCta, 0, st>>>(*scene, *params, d, params->h_uniform);
-      else k_slots<2, false, true><<<ng, kSlotsCta, 0, st>>>(*scene, *params, d, 0.);
+      if (uni) {
+        k_slots<2, true, true><<<ng, kSlotsCta, 0, st>>>(*scene, *params, d, params->h_uniform, thr);
+        k_slots<2, true, false><<<ng, kSlotsCta, 0, st>>>(*scene, *params, d, params->h_uniform, thr);
+      } else {
+        k_slots<2, false, true><<<ng, kSlotsCta, 0, st>>>(*scene, *params, d, 0., thr);
+        k_slots<2, false, false><<<ng, kSlotsCta, 0, st>>>(*scene, *params, d, 0., thr);
+      }
     }
   } else if (scene->dim == 3) {
-    if (uni) k_slots<3, true, false><<<ng, kSlotsCta, 0, st>>>(*scene, *params, d, params->h_uniform);
-    else k_slots<3, false, false><<<ng, kSlotsCta, 0, st>>>(*scene, *params, d, 0.);
+    if (uni) k_slots<3, true, false><<<ng, kSlotsCta, 0, st>>>(*scene, *params, d, params->h_uniform, 0);
+    else k_slots<3, false, false><<<ng, kSlotsCta, 0, st>>>(*scene, *params, d, 0., 0);
   } else {
-    if (uni) k_slots<2, true, false><<<ng, kSlotsCta, 0, st>>>(*scene, *params, d, params->h_uniform);
-    else k_slots<2, false, false><<<ng, kSlotsCta, 0, st>>>(*scene, *params, d, 0.);
+    if (uni) k_slots<2, true, false><<<ng, kSlotsCta, 0, st>>>(*scene, *params, d, params->h_uniform, 0);
+    else k_slots<2, false, false><<<ng, kSlotsCta, 0, st>>>(*scene, *params, d, 0., 0);
   }
   RBX_CHECK_LAUNCH();
   return RBX_OK;

@@ -302,6 +302,9 @@ class DeviceScene(object):
             aux[1:2 * self.n_rigid:2] = \
                 self.B['spacing0'][self.P['body'].long()].float()
         self.T['aux32'] = aux
+        # where the static particles (walls, halo) were at the last list build
+        self.T['static_ref'] = torch.zeros(
+            3 * max(self.n_total - self.n_rigid, 1), dtype=f64, device=dev)
         # evaluations that still have to write every particle (fx = m g and
         # an empty history where nothing is in contact) before the sparse
         # writes can rely on what is in place
@@ -364,6 +367,7 @@ class DeviceScene(object):
             s.gravity[k] = self.g[k]
         s.h_uniform = self.h_uniform
         s.body_tag, s.aux32 = _ptr(T['body_tag']), _ptr(T['aux32'])
+        s.static_ref = _ptr(T['static_ref'])
         for n in ['total_mass', 'izz', 'spacing0', 'xcm', 'vcm', 'ang_mom',
                   'omega', 'force', 'torque', 'R', 'R_prev', 'xcm0', 'vcm0',
                   'ang_mom0', 'R0']:
@@ -409,6 +413,41 @@ class DeviceScene(object):
             _lib.check(self.lib.rbx_pos32_refresh(
                 ctypes.byref(self._scene[0]), 0, self.n_total, self.stream),
                 'rbx_pos32_refresh')
+
+    def static_update(self, name, state, first=0):
+        """New state of (a leading part of) boundary array ``name`` from DEVICE
+        tensors: state = {'x': t, 'y': t, ...} over x, y, z, u, v, w, all of
+        one length.  Asynchronous on the current stream, no host round trip:
+        the neighbour lists are rebuilt only if a particle has moved more
+        than half the skin since they were built (rbx_static_update)."""
+        n = None
+        ptr = {}
+        for k in ('x', 'y', 'z', 'u', 'v', 'w'):
+            t = state.get(k)
+            if t is None:
+                ptr[k] = None
+                continue
+            if t.dtype != torch.float64 or not t.is_cuda or \
+                    not t.is_contiguous():
+                raise ValueError('static_update wants contiguous float64 '
+                                 'CUDA tensors')
+            if n is None:
+                n = int(t.numel())
+            elif n != int(t.numel()):
+                raise ValueError('static_update: tensors differ in length')
+            ptr[k] = t.data_ptr()
+        if not n:
+            return
+        pas = dict((a.name, a) for a in self.bounds)
+        if first < 0 or first + n > pas[name].get_number_of_particles():
+            raise ValueError('static_update: range outside array %s' % name)
+        _lib.check(self.lib.rbx_static_update(
+            ctypes.byref(self.scene), self.p_off[name] + first, n, ptr['x'],
+            ptr['y'], ptr['z'], ptr['u'], ptr['v'], ptr['w'], self.skin,
+            self.stream), 'rbx_static_update')
+        dn = pas[name].__dict__['_device_newer']
+        for k in state:
+            dn.add(k)
 
     def points(self, index=None, n=None):
         p = RbxPoints()
@@ -897,3 +936,95 @@ class DeviceScene(object):
         out = torch.stack([i, j], 1).cpu().numpy().astype(np.int32)
         order = np.lexsort((out[:, 1], out[:, 0]))
         return out[order]
+
+
+class BoundaryStream(object):
+    """Host-driven boundary, streamed: the state of boundary array ``name``
+    for step k + 1 travels host -> device (pinned memory, a copy stream, a
+    staging buffer) while step k computes; ``apply`` hands the staged state to
+    the scene on the compute stream (DeviceScene.static_update).  This is how
+    an Application whose post_step moves a wall every step
+    (stack_of_cylinders.py:438-445 does it once) feeds the device path without
+    stalling it; ``pa.x[:] = ...`` works too, but uploads synchronously from
+    pageable memory and rebuilds the neighbour lists unconditionally."""
+
+    def __init__(self, scene, name, props=('x', 'y', 'z', 'u', 'v', 'w')):
+        self.sc, self.name, self.props = scene, name, tuple(props)
+        pas = dict((a.name, a) for a in scene.bounds)
+        self.n = pas[name].get_number_of_particles()
+        dev = scene.device
+        self.copy_stream = torch.cuda.Stream(dev)
+        self.stage = [dict((p, torch.empty(self.n, dtype=torch.float64,
+                                           device=dev)) for p in self.props)
+                      for _ in range(2)]
+        self.ev_up = [torch.cuda.Event() for _ in range(2)]
+        self.ev_used = [torch.cuda.Event() for _ in range(2)]
+        cur = torch.cuda.current_stream(dev)
+        for e in self.ev_used:
+            e.record(cur)
+        self.k_sub = self.k_app = 0
+        self.bytes_per_submit = 8 * self.n * len(self.props)
+
+    def submit(self, host):
+        """host: {prop: pinned float64 CPU tensor of the array's length}."""
+        k = self.k_sub & 1
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.ev_used[k])  # staging is free
+            for p in self.props:
+                self.stage[k][p].copy_(host[p], non_blocking=True)
+            self.ev_up[k].record(self.copy_stream)
+        self.k_sub += 1
+
+    def apply(self):
+        if self.k_app >= self.k_sub:
+            raise RuntimeError('BoundaryStream.apply without a submit')
+        k = self.k_app & 1
+        cur = torch.cuda.current_stream(self.sc.device)
+        cur.wait_event(self.ev_up[k])
+        self.sc.static_update(self.name, self.stage[k])
+        self.ev_used[k].record(cur)
+        self.k_app += 1
+
+
+class BodyStateStream(object):
+    """Per-body results, streamed the other way: ``snapshot`` copies the named
+    per-body arrays on the compute stream and sends the copy to pinned host
+    memory on a copy stream; ``wait(k)`` returns the host tensors of snapshot
+    k once they have arrived.  Two snapshots can be in flight."""
+
+    def __init__(self, scene, names=('xcm', 'vcm', 'omega', 'R', 'force',
+                                     'torque')):
+        self.sc, self.names = scene, tuple(names)
+        dev = scene.device
+        self.copy_stream = torch.cuda.Stream(dev)
+        self.snap = [dict((n, torch.empty_like(scene.B[n])) for n in names)
+                     for _ in range(2)]
+        self.host = [dict((n, torch.empty_like(scene.B[n],
+                                               device='cpu').pin_memory())
+                          for n in names) for _ in range(2)]
+        self.ev_snap = [torch.cuda.Event() for _ in range(2)]
+        self.ev_out = [torch.cuda.Event() for _ in range(2)]
+        cur = torch.cuda.current_stream(dev)
+        for e in self.ev_out:
+            e.record(cur)
+        self.k = 0
+        self.bytes_per_snapshot = sum(8 * scene.B[n].numel() for n in names)
+
+    def snapshot(self):
+        k = self.k & 1
+        cur = torch.cuda.current_stream(self.sc.device)
+        cur.wait_event(self.ev_out[k])          # snapshot buffer is free
+        for n in self.names:
+            self.snap[k][n].copy_(self.sc.B[n])
+        self.ev_snap[k].record(cur)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.ev_snap[k])
+            for n in self.names:
+                self.host[k][n].copy_(self.snap[k][n], non_blocking=True)
+            self.ev_out[k].record(self.copy_stream)
+        self.k += 1
+        return self.k - 1
+
+    def wait(self, k):
+        self.ev_out[k & 1].synchronize()
+        return self.host[k & 1]

@@ -263,7 +263,8 @@ class SlabScene(object):
         if nr:
             _lib.check(sc.lib.rbx_halo_unpack(
                 ctypes.byref(sc.scene), self.halo_off, nr,
-                self._recv_buf.data_ptr(), sc.stream), 'rbx_halo_unpack')
+                self._recv_buf.data_ptr(), sc.skin, sc.stream),
+                'rbx_halo_unpack')
         self.bytes_sent += ns * HALO_COLS * 8
         self.bytes_recv += nr * HALO_COLS * 8
 
