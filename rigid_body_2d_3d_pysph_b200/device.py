@@ -62,6 +62,15 @@ class DeviceScene(object):
         self.lib = _lib.load()
         self.device = torch.device(device if device is not None else
                                    'cuda:%d' % torch.cuda.current_device())
+        # everything needed to build a scene like this one over other arrays
+        # (parallel.py re-creates the scene when bodies change owner)
+        self._ctor = dict(rigid_names=list(rigid_names),
+                          boundary_names=list(boundary_names), dim=dim, kr=kr,
+                          kf=kf, fric_coeff=fric_coeff, gx=gx, gy=gy, gz=gz,
+                          planar=planar, ks=ks, radius_scale=radius_scale,
+                          eta_uniform=eta_uniform, cap_cells=cap_cells,
+                          list_cap=list_cap, skin_factor=skin_factor,
+                          device=self.device, exact=exact)
         pas = dict((a.name, a) for a in arrays)
         self.rigid = [pas[n] for n in rigid_names]
         self.bounds = [pas[n] for n in boundary_names]

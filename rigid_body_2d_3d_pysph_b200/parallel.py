@@ -15,9 +15,19 @@ re-pose and before the cell-list build.  Received particles land in the
 array to the kernels (scenes.synthetic_pile(halo_cap=...)).
 
 The region of interest is recomputed from the live positions every step, so
-the exchange stays correct even when bodies drift across the initial cuts
-(ownership does not migrate; only the efficiency of the slabs would degrade).
+the exchange stays correct even when bodies drift across the initial cuts.
+Ownership follows them: ``SlabScene.migrate`` hands every body to the rank
+whose interval [cut_k, cut_k+1) holds its centre of mass -- per-body state,
+body-frame vectors and the contact history of its particles travel with it --
+and can move the cuts so that every rank holds the same number of bodies
+again.  It is a rare, host-mediated event (the scene is
+re-created from the merged arrays); ``gtvf_step(..., migrate_every=M)`` checks
+every M steps whether any body has left its slab.
 Static wall particles are replicated per slab when the scene is built.
+
+Backends: NCCL on a multi-GPU box (device tensors go straight into the
+collectives); with gloo -- the CPU tests, and two ranks SHARING one GPU, which
+NCCL refuses -- the payloads are staged through host memory.
 
 Neighbour lists are reused across steps (device.py, skin), so the halo must
 keep its identity between list rebuilds: a *full* exchange (interest intervals
@@ -108,12 +118,141 @@ def exchange_rows(cols, rows, rank, world, group=None):
     return got, int(table[rank].sum()), int(sum(recv_counts)), table
 
 
+def _staged(group=None):
+    """True if device tensors have to go through host memory (gloo)."""
+    return dist.get_backend(group) != 'nccl'
+
+
+# per-body constants of a rigid array (rigid_body_3d.py:781-831) -> stride
+BODY_CONSTS = {'total_mass': 1, 'izz': 1, 'xcm': 3, 'xcm0': 3, 'vcm': 3,
+               'vcm0': 3, 'ang_mom': 3, 'ang_mom0': 3, 'omega': 3,
+               'omega0': 3, 'force': 3, 'torque': 3, 'R': 9, 'R0': 9,
+               'inertia_tensor_body_frame': 9,
+               'inertia_tensor_inverse_body_frame': 9,
+               'inertia_tensor_global_frame': 9,
+               'inertia_tensor_inverse_global_frame': 9}
+
+
+def body_strides(pa):
+    nb = int(pa.constants['nb'][0])
+    tnb = int(pa.constants['total_no_bodies'][0])
+    st = dict((k, v) for k, v in BODY_CONSTS.items() if k in pa.constants)
+    for k in ('eta', 'coeff_of_rest'):
+        if k in pa.constants and pa.constants[k].size == nb * tnb:
+            st[k] = tnb
+    return st
+
+
+def take_bodies(pa, bodies, hist=None):
+    """The bodies (local indices, ascending) of rigid array ``pa`` as a
+    picklable payload: per-particle properties, per-body constants, and --
+    hist = (key [ks, n], dlt [3, ks, n], fn [3, ks, n]) -- the contact
+    history of their particles."""
+    bodies = np.asarray(bodies, dtype=np.int64)
+    bid = pa.properties['body_id']
+    sel = np.nonzero(np.isin(bid, bodies))[0]
+    out = {'props': {}, 'consts': {}, 'nb': int(bodies.size)}
+    for name, arr in pa.properties.items():
+        s = pa.stride[name]
+        out['props'][name] = arr.reshape(-1, s)[sel].ravel().copy()
+    for name, s in body_strides(pa).items():
+        out['consts'][name] = \
+            pa.constants[name].reshape(-1, s)[bodies].ravel().copy()
+    # bodies are identified by their dem_id across ranks
+    first = np.searchsorted(bid, bodies)
+    out['dem'] = pa.properties['dem_id'][first].astype(np.int64)
+    out['count'] = np.bincount(np.searchsorted(bodies, bid[sel]),
+                               minlength=bodies.size).astype(np.int64)
+    if hist is not None:
+        key, dlt, fn = hist
+        out['hist'] = (key[:, sel].copy(), dlt[:, :, sel].copy(),
+                       fn[:, :, sel].copy())
+    return out
+
+
+def merge_bodies(template, parts):
+    """A rigid ParticleArray like ``template`` holding the bodies of the
+    payloads ``parts`` in ascending dem_id order, and their history."""
+    from .compat.particle_array import ParticleArray
+    parts = [p for p in parts if p['nb'] > 0]
+    dem = np.concatenate([p['dem'] for p in parts]) if parts else \
+        np.zeros(0, np.int64)
+    cnt = np.concatenate([p['count'] for p in parts]) if parts else \
+        np.zeros(0, np.int64)
+    order = np.argsort(dem, kind='stable')
+    nb = int(dem.size)
+    # particle permutation: bodies in `order`, particles of a body as they were
+    start = np.cumsum(cnt) - cnt
+    pidx = np.concatenate([np.arange(start[b], start[b] + cnt[b])
+                           for b in order]) if nb else np.zeros(0, np.int64)
+    new = ParticleArray(name=template.name)
+    new.__dict__['_n'] = int(pidx.size)
+    for name in template.properties:
+        s = template.stride[name]
+        cat = np.concatenate([p['props'][name] for p in parts]) if parts \
+            else np.zeros(0, template.properties[name].dtype)
+        new.add_property(name, type=template.property_types[name],
+                         data=cat.reshape(-1, s)[pidx].ravel(), stride=s)
+    new.properties['body_id'][:] = np.repeat(
+        np.arange(nb, dtype=np.int32), cnt[order])
+    st = body_strides(template)
+    for name, val in template.constants.items():
+        if name in st:
+            s = st[name]
+            cat = np.concatenate([p['consts'][name] for p in parts]) \
+                if parts else np.zeros(0)
+            new.add_constant(name, cat.reshape(-1, s)[order].ravel())
+        elif name == 'nb':
+            new.add_constant('nb', nb)
+        elif name in ('min_dem_id', 'max_dem_id') and nb:
+            new.add_constant(name, int(dem.min() if name == 'min_dem_id'
+                                       else dem.max()))
+        else:
+            new.add_constant(name, val)
+    new.set_output_arrays(list(template.output_property_arrays))
+    hist = None
+    if parts and all('hist' in p for p in parts):
+        key = np.concatenate([p['hist'][0] for p in parts], 1)[:, pidx]
+        dlt = np.concatenate([p['hist'][1] for p in parts], 2)[:, :, pidx]
+        fn = np.concatenate([p['hist'][2] for p in parts], 2)[:, :, pidx]
+        hist = (key, dlt, fn)
+    return new, hist
+
+
+def balanced_cuts(xcm_all, world):
+    """Cut planes that give every rank the same number of bodies (+-1):
+    midpoints between the neighbours in the sorted centre-of-mass
+    coordinates; -inf / +inf at the ends."""
+    xs = np.sort(np.asarray(xcm_all, dtype=np.float64))
+    cuts = [-np.inf]
+    for k in range(1, world):
+        i = (k * xs.size) // world
+        cuts.append(0.5 * (xs[i - 1] + xs[i]) if 0 < i < xs.size else
+                    (xs[0] if xs.size else 0.))
+    cuts.append(np.inf)
+    return np.array(cuts)
+
+
 class SlabScene(object):
     """A DeviceScene that is one x-slab of a larger scene."""
 
-    def __init__(self, scene, rank, world, group=None, halo_name='halo'):
-        self.sc = scene
+    def __init__(self, scene, rank, world, group=None, halo_name='halo',
+                 cuts=None):
         self.rank, self.world, self.group = rank, world, group
+        self.halo_name = halo_name
+        self.staged = world > 1 and _staged(group)
+        # ownership intervals [cuts[k], cuts[k+1]) along x; None until the
+        # first migrate() (ownership = where the scene builder put the body)
+        self.cuts = None if cuts is None else np.asarray(cuts, np.float64)
+        self.bytes_sent = 0
+        self.bytes_recv = 0
+        self.migrations = 0
+        self.bodies_moved = 0
+        self._bind(scene)
+
+    def _bind(self, scene):
+        self.sc = scene
+        halo_name = self.halo_name
         pas = dict((a.name, a) for a in scene.arrays)
         self.halo_off = scene.p_off[halo_name]
         self.halo_cap = pas[halo_name].get_number_of_particles()
@@ -134,9 +273,46 @@ class SlabScene(object):
         self._send_idx = None
         self._send_counts = self._recv_counts = None
         self._send_buf = self._recv_buf = None
-        self.bytes_sent = 0
-        self.bytes_recv = 0
         self._set_source_count(0)
+
+    # -- collectives, staged through host memory under gloo -------------------
+    def _all_reduce_max(self, t):
+        if self.staged:
+            h = t.cpu()
+            dist.all_reduce(h, op=dist.ReduceOp.MAX, group=self.group)
+            t.copy_(h)
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+
+    def _all_gather(self, t):
+        src = t.cpu() if self.staged else t
+        out = [torch.empty_like(src) for _ in range(self.world)]
+        dist.all_gather(out, src, group=self.group)
+        return torch.stack(out)
+
+    def _p2p(self, send, recv, send_counts, recv_counts):
+        """send[q] -> rank q, recv[q] <- rank q (lists of [m, HALO_COLS]
+        device tensors, empty ones skipped)."""
+        if self.staged:
+            hs = [t.cpu() for t in send]
+            hr = [torch.empty(t.shape, dtype=t.dtype) for t in recv]
+        else:
+            hs, hr = send, recv
+        ops = []
+        for q in range(self.world):
+            if q == self.rank:
+                continue
+            if send_counts[q] > 0:
+                ops.append(dist.P2POp(dist.isend, hs[q], q, self.group))
+            if recv_counts[q] > 0:
+                ops.append(dist.P2POp(dist.irecv, hr[q], q, self.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        if self.staged:
+            for q in range(self.world):
+                if q != self.rank and recv_counts[q] > 0:
+                    recv[q].copy_(hr[q])
 
     def _set_source_count(self, n_halo):
         self.n_halo = n_halo
@@ -147,7 +323,7 @@ class SlabScene(object):
         rank moved more than half the skin since the lists were built?"""
         flag = self.sc.rebuild
         if self.world > 1:
-            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
+            self._all_reduce_max(flag)
         return bool(flag.item() != 0)          # host sync
 
     def exchange_halo(self, full=True):
@@ -163,9 +339,7 @@ class SlabScene(object):
             return
         iv = interest_interval(P['x'][:sc.n_rigid], sc.reach + sc.skin)
         if self.world > 1:
-            ivs = [torch.empty_like(iv) for _ in range(self.world)]
-            dist.all_gather(ivs, iv, group=self.group)
-            ivs = torch.stack(ivs)
+            ivs = self._all_gather(iv)
         else:
             ivs = iv[None, :]
         ivh = ivs.cpu()                      # host sync (2 doubles / rank)
@@ -200,8 +374,7 @@ class SlabScene(object):
         rel = [torch.arange(int(offs[q]), int(offs[q + 1]), device=dev)
                for q in range(self.world)]
         if self.world > 1:
-            got, ns, nr, table = exchange_rows(cols, rel, self.rank,
-                                               self.world, self.group)
+            got, ns, nr, table = self._exchange_rows(cols, rel)
         else:
             got, ns, nr, table = cols[:0], 0, 0, None
         if nr > self.halo_cap:
@@ -216,6 +389,22 @@ class SlabScene(object):
         self._set_source_count(nr)
         self.bytes_sent += ns * HALO_COLS * 8
         self.bytes_recv += nr * HALO_COLS * 8
+
+    def _exchange_rows(self, cols, rows):
+        """exchange_rows through this scene's backend."""
+        dev = cols.device
+        counts = torch.tensor([r.numel() for r in rows], dtype=torch.int64,
+                              device=dev)
+        table = self._all_gather(counts).cpu()     # [src, dst] (host sync)
+        recv_counts = [int(table[q, self.rank]) for q in range(self.world)]
+        send_counts = [int(table[self.rank, q]) for q in range(self.world)]
+        recv = [torch.empty(recv_counts[q], cols.shape[1], dtype=cols.dtype,
+                            device=dev) for q in range(self.world)]
+        send = [cols.index_select(0, rows[q]).contiguous()
+                for q in range(self.world)]
+        self._p2p(send, recv, send_counts, recv_counts)
+        got = torch.cat(recv, 0) if recv else cols[:0]
+        return got, int(table[self.rank].sum()), int(sum(recv_counts)), table
 
     def _pack(self, gsel):
         P = self.sc.P
@@ -247,19 +436,9 @@ class SlabScene(object):
             _lib.check(sc.lib.rbx_halo_pack(
                 ctypes.byref(sc.scene), self._send_idx.data_ptr(), ns,
                 self._send_buf.data_ptr(), sc.stream), 'rbx_halo_pack')
-        send = torch.split(self._send_buf, self._send_counts, 0)
-        recv = torch.split(self._recv_buf, self._recv_counts, 0)
-        ops = []
-        for q in range(self.world):
-            if q == self.rank:
-                continue
-            if self._send_counts[q] > 0:
-                ops.append(dist.P2POp(dist.isend, send[q], q, self.group))
-            if self._recv_counts[q] > 0:
-                ops.append(dist.P2POp(dist.irecv, recv[q], q, self.group))
-        if ops:
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
+        send = list(torch.split(self._send_buf, self._send_counts, 0))
+        recv = list(torch.split(self._recv_buf, self._recv_counts, 0))
+        self._p2p(send, recv, self._send_counts, self._recv_counts)
         if nr:
             _lib.check(sc.lib.rbx_halo_unpack(
                 ctypes.byref(sc.scene), self.halo_off, nr,
@@ -268,9 +447,107 @@ class SlabScene(object):
         self.bytes_sent += ns * HALO_COLS * 8
         self.bytes_recv += nr * HALO_COLS * 8
 
-    def gtvf_step(self, dt, nsteps=1):
+    # -- ownership ------------------------------------------------------------
+    def bodies_outside(self):
+        """How many of this rank's bodies have their centre of mass outside
+        its ownership interval (0 before the first migrate(): no cuts yet)."""
+        if self.cuts is None:
+            return 0
+        nb = self.sc.n_bodies
+        x = self.sc.B['xcm'][0:3 * nb:3]
+        lo, hi = float(self.cuts[self.rank]), float(self.cuts[self.rank + 1])
+        return int(((x < lo) | (x >= hi)).sum().item())
+
+    def migrate(self, rebalance=False, cuts=None):
+        """Hand every body to the rank whose interval holds its centre of mass
+        (SURVEY 8e step 5): per-body state, body-frame vectors, and the contact
+        history of its particles move; the device scene is re-created from
+        the merged arrays and the next step does a full halo exchange.
+
+        cuts: world + 1 ascending cut planes (first -inf, last +inf);
+        rebalance=True: place them so that every rank holds the same number
+        of bodies (balanced_cuts); neither: keep the current ones (the first
+        call then balances).  Collective.  Returns the number of bodies this
+        rank received."""
+        from .device import DeviceScene
+        sc = self.sc
+        if len(sc.rigid) != 1:
+            raise NotImplementedError('migration handles one rigid array')
+        pa = sc.rigid[0]
+        sc.sync_to_host()
+        hist = sc.history()
+        nb = int(pa.constants['nb'][0])
+        xcm_x = np.asarray(pa.constants['xcm'])[0:3 * nb:3].copy()
+        if cuts is not None:
+            self.cuts = np.asarray(cuts, np.float64)
+        elif rebalance or self.cuts is None:
+            allx = [None] * self.world
+            dist.all_gather_object(allx, xcm_x, group=self.group)
+            self.cuts = balanced_cuts(np.concatenate(allx), self.world)
+        owner = np.searchsorted(self.cuts[1:-1], xcm_x, side='right')
+        out = []
+        for q in range(self.world):
+            b = np.nonzero(owner == q)[0]
+            out.append(take_bodies(pa, b, hist))
+        # everybody sees everybody's parcels and takes its own (the parcels
+        # are a few bodies; a rare event)
+        mine = out[self.rank]
+        parcels = [out[q] if q != self.rank else None
+                   for q in range(self.world)]
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, parcels, group=self.group)
+        incoming = [gathered[src][self.rank] for src in range(self.world)
+                    if src != self.rank]
+        received = sum(p['nb'] for p in incoming)
+        moved = nb - mine['nb']
+        tot = torch.tensor([received + moved], dtype=torch.int64)
+        if dist.get_backend(self.group) == 'nccl':
+            tot = tot.to(self.sc.device)
+        dist.all_reduce(tot, group=self.group)
+        self.migrations += 1
+        self.bodies_moved += moved
+        if int(tot.item()) == 0:
+            return 0                       # nobody moved: keep the scene
+        new_pa, new_hist = merge_bodies(pa, [mine] + incoming)
+        arrays = [new_pa] + [a for a in sc.arrays if a is not pa]
+        for a in arrays[1:]:
+            a.__dict__['_device'] = None
+        kw = dict(sc._ctor)
+        rigid_names, boundary_names = kw.pop('rigid_names'), \
+            kw.pop('boundary_names')
+        steps_done = sc.steps_done
+        del hist
+        self.sc = None
+        sc = None
+        torch.cuda.empty_cache()
+        new_sc = DeviceScene(arrays, rigid_names, boundary_names, **kw)
+        new_sc.steps_done = steps_done
+        if new_hist is not None and new_pa.get_number_of_particles():
+            new_sc.set_history(new_pa.name, *new_hist)
+        self._bind(new_sc)
+        return received
+
+    def gtvf_step(self, dt, nsteps=1, migrate_every=0):
         """GTVFIntegrator.one_timestep with the halo exchange between the
-        re-pose (stage 2) and the force evaluation."""
+        re-pose (stage 2) and the force evaluation.  migrate_every = M > 0:
+        every M steps, if a body of any rank has left its slab, ownership
+        migrates (cuts are kept; the first time they are count-balanced)."""
+        if migrate_every and self.world > 1:
+            done = 0
+            while done < nsteps:
+                n = min(migrate_every - self.sc.steps_done % migrate_every,
+                        nsteps - done)
+                self.gtvf_step(dt, n)
+                done += n
+                if self.sc.steps_done % migrate_every == 0:
+                    away = torch.tensor([self.bodies_outside() if self.cuts
+                                         is not None else 1])
+                    if dist.get_backend(self.group) == 'nccl':
+                        away = away.to(self.sc.device)
+                    dist.all_reduce(away, group=self.group)
+                    if int(away.item()) > 0:
+                        self.migrate()
+            return
         sc = self.sc
         sc.push_touched()
         for k in range(nsteps):

@@ -2,6 +2,14 @@
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 \
         --master-addr 127.0.0.1 --master-port 29511 tests/mgpu_equiv.py
+
+With fewer GPUs than ranks the ranks share GPU 0 and talk over gloo (NCCL
+refuses two ranks on one device): the same slab code, payloads staged through
+host memory -- this is how the 1-GPU test box runs it.
+
+MGPU_LATERAL = v > 0: every body starts with vcm_x = v, so whole columns of
+bodies cross the cut between the slabs; ownership migrates every MGPU_MIGRATE
+steps (SlabScene.migrate) and the run must still equal the single-rank one.
 """
 import os
 import sys
@@ -29,10 +37,14 @@ DT = 1e-4
 # one.
 MU = float(os.environ.get('MGPU_MU', '0.0'))
 EXACT_STEPS = int(os.environ.get('MGPU_EXACT', '100000' if MU == 0.0 else '0'))
+LATERAL = float(os.environ.get('MGPU_LATERAL', '0'))
+MIGRATE = int(os.environ.get('MGPU_MIGRATE', '50' if LATERAL else '0'))
 
 
 def scene_of(arrays, info, dev):
     names = [a.name for a in arrays]
+    if LATERAL:
+        arrays[0].vcm[0::3] = LATERAL
     return DeviceScene(arrays, ['body'], names[1:], dim=3, gy=-9.81,
                        fric_coeff=MU, eta_uniform=info['eta_uniform'],
                        device=dev)
@@ -42,9 +54,15 @@ def main():
     rank = int(os.environ['RANK'])
     world = int(os.environ['WORLD_SIZE'])
     local = int(os.environ.get('LOCAL_RANK', '0'))
+    ngpu = torch.cuda.device_count()
+    shared = ngpu < world
+    local = local % max(ngpu, 1)
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
-    dist.init_process_group('nccl', device_id=dev)
+    if shared:
+        dist.init_process_group('gloo')
+    else:
+        dist.init_process_group('nccl', device_id=dev)
     arrays, _, info = synthetic_pile(NB, slab=(rank, world), halo_cap=200000)
     sc = scene_of(arrays, info, dev)
     slab = SlabScene(sc, rank, world)
@@ -53,6 +71,7 @@ def main():
         full, _, finfo = synthetic_pile(NB, slab=(0, world), span=world)
         one = scene_of(full, finfo, dev)
     ok = True
+    seen_contact = False
     done = 0
     checks = [c for c in (50, 100, 200, 300, 400, 500, 600, 700, 1000, 1500)
               if c <= STEPS]
@@ -61,14 +80,19 @@ def main():
     for upto in checks:
         n = upto - done
         done = upto
-        slab.gtvf_step(DT, n)
+        slab.gtvf_step(DT, n, migrate_every=MIGRATE)
+        sc = slab.sc                     # a migration re-creates the scene
         sc.check_status()
-        mine = torch.cat([sc.B['xcm'], sc.B['R'], sc.B['vcm'], sc.B['omega']])
-        parts = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(parts, mine)
-        halo_bytes = torch.tensor([slab.bytes_recv], dtype=torch.float64,
-                                  device=dev)
-        dist.all_reduce(halo_bytes)
+        nbl = sc.n_bodies
+        first = sc.T['chunk_start'][sc.T['body_chunk'][:nbl].long()].long()
+        mine = {'dem': sc.P['dem_id'][first].cpu().numpy(),
+                'halo': slab.bytes_recv, 'moved': slab.bodies_moved}
+        for name in ('xcm', 'R', 'vcm', 'omega'):
+            mine[name] = sc.B[name].cpu().numpy()
+        parts = [None] * world
+        dist.all_gather_object(parts, mine)
+        halo_bytes = sum(p_['halo'] for p_ in parts)
+        moved = sum(p_['moved'] for p_ in parts)
         if rank == 0:
             for _ in range(n):
                 one.gtvf_kick(DT)
@@ -81,22 +105,24 @@ def main():
                 one.gtvf_kick(DT)
                 one.pose(_lib.POSE_VEL)
             one.check_status()
-            nb = NB
             errs = {}
-            for k, (name, s) in enumerate([('xcm', 3), ('R', 9), ('vcm', 3),
-                                           ('omega', 3)]):
-                got = []
-                for q in range(world):
-                    off = sum(x * nb for x in (3, 9, 3, 3)[:k])
-                    got.append(parts[q][off:off + s * nb])
-                got = torch.cat(got).cpu().numpy()
+            dem = np.concatenate([p_['dem'] for p_ in parts])
+            assert np.array_equal(np.sort(dem), np.arange(NB * world)), \
+                'bodies lost or duplicated'
+            for name, s in (('xcm', 3), ('R', 9), ('vcm', 3), ('omega', 3)):
+                got = np.empty(s * NB * world)
+                got.reshape(-1, s)[dem] = np.concatenate(
+                    [p_[name] for p_ in parts]).reshape(-1, s)
                 want = one.B[name].cpu().numpy()
                 errs[name] = float(np.abs(got - want).max())
             cnt = one.read_counters(reset=True)
-            print('mgpu_equiv world=%d bodies=%d step=%d active_slots/step='
-                  '%.0f halo_bytes/step=%.0f max errors %s' % (
-                      world, NB * world, upto, cnt['active_slots'] / n,
-                      float(halo_bytes) / upto,
+            print('mgpu_equiv world=%d%s bodies=%d step=%d active_slots/step='
+                  '%.0f halo_bytes/step=%.0f migrated=%d bodies per rank %s '
+                  'max errors %s' % (
+                      world, ' (one GPU, gloo)' if shared else '', NB * world,
+                      upto, cnt['active_slots'] / n,
+                      float(halo_bytes) / upto, moved,
+                      [int(p_['dem'].size) for p_ in parts],
                       dict((k, '%.1e' % v) for k, v in errs.items())),
                   flush=True)
             # contacts are chaotic (quirk Q1): hold the tight bound over the
@@ -105,7 +131,11 @@ def main():
                 ok = ok and errs['xcm'] < 1e-9 and errs['R'] < 1e-8
             else:
                 ok = ok and errs['xcm'] < 1e-3
-            ok = ok and cnt['active_slots'] > 0
+            seen_contact = seen_contact or cnt['active_slots'] > 0
+            if upto == checks[-1]:
+                ok = ok and seen_contact     # the run did reach contact
+                if LATERAL:
+                    ok = ok and moved > 0    # bodies did change owner
     if rank == 0:
         print('MGPU_EQUIV_OK' if ok else 'MGPU_EQUIV_FAIL', flush=True)
     dist.barrier()

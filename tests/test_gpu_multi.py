@@ -1,4 +1,6 @@
-"""2-rank slab decomposition on real GPUs (NCCL): skipped on a 1-GPU box."""
+"""2-rank slab decomposition against the single-rank run: over NCCL on a
+multi-GPU box, over gloo with both ranks on GPU 0 otherwise (so the 1-GPU
+test box runs it too), with and without bodies that change owner."""
 import os
 import subprocess
 import sys
@@ -10,13 +12,28 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_two_rank_run_equals_single_rank():
-    import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip('needs 2 GPUs')
+def _run(port, **env):
+    e = dict(os.environ)
+    e.update(dict((k, str(v)) for k, v in env.items()))
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1',
            '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
-           '--master-port', '29517', os.path.join(ROOT, 'tests',
-                                                  'mgpu_equiv.py')]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
-    assert 'MGPU_EQUIV_OK' in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+           '--master-port', str(port), os.path.join(ROOT, 'tests',
+                                                    'mgpu_equiv.py')]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900,
+                         env=e)
+    assert 'MGPU_EQUIV_OK' in out.stdout, \
+        out.stdout[-3000:] + out.stderr[-3000:]
+    return out.stdout
+
+
+def test_two_rank_run_equals_single_rank():
+    _run(29517, MGPU_BODIES=600, MGPU_STEPS=700)
+
+
+def test_two_rank_run_with_migrating_bodies_equals_single_rank():
+    """Every body starts with vcm_x = 3 m/s: a column of bodies crosses the
+    cut, ownership migrates (state, body-frame vectors, contact history), and
+    the run still equals the single-rank one (frictionless, 1e-9)."""
+    out = _run(29519, MGPU_BODIES=600, MGPU_STEPS=700, MGPU_LATERAL=3.0,
+               MGPU_MIGRATE=50)
+    assert 'migrated=0 ' not in out.splitlines()[-2]

@@ -123,3 +123,45 @@ def test_body_level_selection_equals_full_scan():
         got = parallel.select_sources_by_body(x, own_src, start, cnt, xcm,
                                               rmax, lo, hi)
         assert torch.equal(got, want), (lo, hi, got.numel(), want.numel())
+
+
+def test_body_parcels_round_trip_and_balanced_cuts():
+    """Host side of SlabScene.migrate: bodies taken out of a rigid array as
+    parcels (properties, per-body constants, contact history) and merged back
+    in another grouping give the original array, ordered by dem_id; cuts
+    placed by balanced_cuts give every rank the same number of bodies."""
+    from rigid_body_2d_3d_pysph_b200 import parallel
+    (body, wall), _, info = synthetic_pile(12, seed=3)
+    n = body.get_number_of_particles()
+    nb = int(body.nb[0])
+    rng = np.random.default_rng(0)
+    body.vcm[:] = rng.normal(size=3 * nb)
+    body.R[:] = rng.normal(size=9 * nb)
+    ks = 4
+    key = rng.integers(-1, 5, size=(ks, n)).astype(np.int32)
+    dlt = rng.normal(size=(3, ks, n))
+    fn = rng.normal(size=(3, ks, n))
+    a = parallel.take_bodies(body, [0, 3, 4, 11], (key, dlt, fn))
+    b = parallel.take_bodies(body, [1, 2, 5, 6, 7, 8, 9, 10], (key, dlt, fn))
+    assert a['nb'] == 4 and b['nb'] == 8
+    merged, hist = parallel.merge_bodies(body, [b, a])
+    assert merged.get_number_of_particles() == n
+    assert int(merged.nb[0]) == nb
+    for name in body.properties:
+        assert np.array_equal(merged.properties[name], body.properties[name]), name
+    for name in parallel.body_strides(body):
+        assert np.array_equal(merged.constants[name], body.constants[name]), name
+    assert np.array_equal(hist[0], key) and np.array_equal(hist[1], dlt)
+    assert np.array_equal(hist[2], fn)
+    # a subset: bodies renumbered 0.., dem_id kept
+    sub, _ = parallel.merge_bodies(body, [a])
+    assert int(sub.nb[0]) == 4
+    assert np.array_equal(np.unique(sub.body_id), np.arange(4))
+    assert np.array_equal(np.unique(sub.dem_id), [0, 3, 4, 11])
+    assert np.array_equal(sub.xcm, body.xcm.reshape(-1, 3)[[0, 3, 4, 11]].ravel())
+    # cuts
+    x = rng.uniform(0, 10, 1001)
+    cuts = parallel.balanced_cuts(x, 4)
+    owner = np.searchsorted(cuts[1:-1], x, side='right')
+    cnt = np.bincount(owner, minlength=4)
+    assert cnt.max() - cnt.min() <= 1 and cuts[0] == -np.inf
