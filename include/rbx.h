@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RBX_VERSION 402 /* 0.4.2 */
+#define RBX_VERSION 403 /* 0.4.3 */
 
 typedef enum {
   RBX_OK = 0,
@@ -384,10 +384,14 @@ int rbx_static_update(const RbxScene *scene, int32_t first, int32_t n,
 
 /* Multi-GPU halo payload (no counterpart in the reference, which is single
  * process): rows of 8 doubles {x, y, z, u, v, w, h, dem_id}.  pack gathers
- * the particles index[0..n) into rows[n][8]; unpack writes rows[n][8] into
- * the particles [first, first + n) (a static source array of the scene).   */
+ * the particles index[0..n) into rows[n][8] (body_vel != 0: the velocity of
+ * a body particle is its stage-1 velocity formed from the body state, as
+ * under RBX_PARAM_BODY_VEL); unpack writes rows[n][8] into the particles
+ * [first, first + n) (a static source array of the scene) and raises
+ * `rebuild` if one of them has moved more than skin / 2 since the lists
+ * were built.                                                              */
 int rbx_halo_pack(const RbxScene *scene, const int64_t *index, int32_t n,
-                  double *rows, void *stream);
+                  double *rows, int body_vel, void *stream);
 int rbx_halo_unpack(const RbxScene *scene, int32_t first, int32_t n,
                     const double *rows, double skin, void *stream);
 
@@ -423,7 +427,10 @@ int rbx_boundary_identify(const RbxPoints *pts, const RbxCells *cells, int dim,
  * `src` = the source points (contact_force_is_boundary == 1) to bin.
  * flags: bit0 = skip the final particle-velocity / boundary-normal write
  * (inside a batch of steps nothing reads them: stage 1 of the next step
- * overwrites the velocities, and the normals are a function of R alone)     */
+ * overwrites the velocities, and the normals are a function of R alone);
+ * bit1 = only the part before the force evaluation (kick, drift, positions),
+ * bit2 = only the part from the cell list on -- a multi-GPU caller puts its
+ * halo exchange between the two                                             */
 int rbx_gtvf_step(const RbxScene *scene, const RbxPoints *src,
                   const RbxCells *cells, const RbxParams *params,
                   void *workspace, size_t workspace_bytes, int flags,

@@ -159,7 +159,8 @@ def load():
     L.rbx_gtvf_drift.argtypes = [P(RbxScene), c_f64, c_f64, c_vp]
     L.rbx_pose_particles.argtypes = [P(RbxScene), ctypes.c_int, c_vp]
     L.rbx_pos32_refresh.argtypes = [P(RbxScene), c_i32, c_i32, c_vp]
-    L.rbx_halo_pack.argtypes = [P(RbxScene), c_vp, c_i32, c_vp, c_vp]
+    L.rbx_halo_pack.argtypes = [P(RbxScene), c_vp, c_i32, c_vp, ctypes.c_int,
+                                c_vp]
     L.rbx_halo_unpack.argtypes = [P(RbxScene), c_i32, c_i32, c_vp, c_f64,
                                   c_vp]
     L.rbx_static_update.argtypes = [P(RbxScene), c_i32, c_i32, c_vp, c_vp,

@@ -255,11 +255,22 @@ __global__ void __launch_bounds__(256) k_pose(RbxScene S, int flags) {
 }
 
 // halo payload rows {x, y, z, u, v, w, h, dem_id}: thread <-> (particle, column)
-__global__ void k_halo_pack(RbxScene S, const int64_t *index, int n, double *rows) {
+__global__ void k_halo_pack(RbxScene S, const int64_t *index, int n, double *rows,
+                            int body_vel) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n * 8) return;
   const int c = k & 7;
   const long long q = index[k >> 3];
+  if (body_vel && c >= 3 && c < 6 && q < S.n_rigid) {
+    // stage-1 velocity of a body particle, formed here: u, v, w are not kept
+    // current inside a step (RBX_PARAM_BODY_VEL)
+    const int b = S.body[q];
+    double uvw[3];
+    rbx_point_velocity(S.R_prev + 9 * b, S.omega + 3 * b, S.vcm + 3 * b, S.dx0[q], S.dy0[q],
+                       S.dz0[q], uvw[0], uvw[1], uvw[2]);
+    rows[k] = uvw[c - 3];
+    return;
+  }
   const double *col[7] = {S.x, S.y, S.z, S.u, S.v, S.w, S.h};
   rows[k] = c < 7 ? col[c][q] : (double)S.dem_id[q];
 }
@@ -349,10 +360,11 @@ extern "C" int rbx_pose_particles(const RbxScene *scene, int flags, void *stream
 }
 
 extern "C" int rbx_halo_pack(const RbxScene *scene, const int64_t *index, int32_t n,
-                             double *rows, void *stream) {
+                             double *rows, int body_vel, void *stream) {
   if (!scene || n < 0 || (n > 0 && (!index || !rows))) return RBX_ERR_INVALID;
+  if (body_vel && !scene->R_prev) return RBX_ERR_INVALID;
   if (n == 0) return RBX_OK;
-  k_halo_pack<<<rbx_blocks((long long)n * 8, 256), 256, 0, (cudaStream_t)stream>>>(*scene, index, n, rows);
+  k_halo_pack<<<rbx_blocks((long long)n * 8, 256), 256, 0, (cudaStream_t)stream>>>(*scene, index, n, rows, body_vel);
   RBX_CHECK_LAUNCH();
   return RBX_OK;
 }
@@ -397,26 +409,31 @@ extern "C" int rbx_gtvf_step(const RbxScene *scene, const RbxPoints *src, const 
                              const RbxParams *params, void *workspace, size_t workspace_bytes,
                              int flags, void *stream) {
   if (!scene || !src || !cells || !params) return RBX_ERR_INVALID;
-  cudaStream_t st = (cudaStream_t)stream;
-  int rc;
-  if ((rc = launch_bodies(scene, 8 | 4, params->dt, params->skin, st))) return rc;
-  // Positions only.  The stage-1 velocities (post-kick omega, pre-drift R)
-  // are needed for the ~1 % of the particles in contact, which the contact
-  // law forms itself (RBX_PARAM_BODY_VEL); u, v, w and the rotated normals
-  // are written once, at the end of the step.
   if (!scene->R_prev) return RBX_ERR_INVALID;
-  RbxParams par = *params;
-  par.flags |= RBX_PARAM_BODY_VEL;
-  if ((rc = rbx_pose_particles(scene, RBX_POSE_POS, stream))) return rc;
-  if ((rc = rbx_cells_build(src, cells, params->reach, scene->status, workspace,
-                            workspace_bytes, stream))) return rc;
-  if ((rc = rbx_contact_mofidi(scene, cells, &par, nullptr, stream))) return rc;
-  // reduce (k_reduce, warp per body) and kick (k_bodies, thread per body)
-  // are two launches: with the kick's divisions on lane 0 of every reduce
-  // warp, the warp sat on its slot three times longer than its loads take
-  if ((rc = launch_bodies(scene, 1 | 2, params->dt, 0., st))) return rc;
-  if (!(flags & 1))
-    if ((rc = rbx_pose_particles(scene, RBX_POSE_VEL | RBX_POSE_NORMALS, stream))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool pre = !(flags & 4), post = !(flags & 2);
+  int rc;
+  if (pre) {
+    if ((rc = launch_bodies(scene, 8 | 4, params->dt, params->skin, st))) return rc;
+    // Positions only.  The stage-1 velocities (post-kick omega, pre-drift R)
+    // are needed for the ~1 % of the particles in contact, which the contact
+    // law forms itself (RBX_PARAM_BODY_VEL); u, v, w and the rotated normals
+    // are written once, at the end of the step.
+    if ((rc = rbx_pose_particles(scene, RBX_POSE_POS, stream))) return rc;
+  }
+  if (post) {
+    RbxParams par = *params;
+    par.flags |= RBX_PARAM_BODY_VEL;
+    if ((rc = rbx_cells_build(src, cells, params->reach, scene->status, workspace,
+                              workspace_bytes, stream))) return rc;
+    if ((rc = rbx_contact_mofidi(scene, cells, &par, nullptr, stream))) return rc;
+    // reduce (k_reduce, warp per body) and kick (k_bodies, thread per body)
+    // are two launches: with the kick's divisions on lane 0 of every reduce
+    // warp, the warp sat on its slot three times longer than its loads take
+    if ((rc = launch_bodies(scene, 1 | 2, params->dt, 0., st))) return rc;
+    if (!(flags & 1))
+      if ((rc = rbx_pose_particles(scene, RBX_POSE_VEL | RBX_POSE_NORMALS, stream))) return rc;
+  }
   return RBX_OK;
 }
 

@@ -708,12 +708,13 @@ class DeviceScene(object):
                                           int(stage), float(dt), int(fix_q7),
                                           self.skin, self.stream), 'rk2')
 
-    def _gtvf_step_call(self, p, flags=0):
+    def _gtvf_step_call(self, p, flags=0, evaluated=True):
         _lib.check(self.lib.rbx_gtvf_step(
             ctypes.byref(self.scene), ctypes.byref(self._src),
             ctypes.byref(self._cells), ctypes.byref(p), _ptr(self.workspace),
             self.workspace.numel(), int(flags), self.stream), 'rbx_gtvf_step')
-        self._evaluated()
+        if evaluated:           # (the first half of a split step is not one)
+            self._evaluated()
 
     def gtvf_step(self, dt, nsteps=1, graph=False):
         """nsteps x GTVFIntegrator.one_timestep on the device."""

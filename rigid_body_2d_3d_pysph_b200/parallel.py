@@ -407,10 +407,18 @@ class SlabScene(object):
         return got, int(table[self.rank].sum()), int(sum(recv_counts)), table
 
     def _pack(self, gsel):
-        P = self.sc.P
-        return torch.stack([P['x'][gsel], P['y'][gsel], P['z'][gsel],
-                            P['u'][gsel], P['v'][gsel], P['w'][gsel],
-                            P['h'][gsel], P['dem_id'][gsel].double()], 1)
+        """rows {x, y, z, u, v, w, h, dem_id} of the particles gsel; the
+        velocities are the stage-1 velocities formed from the body state
+        (u, v, w are not kept current inside a step)."""
+        import ctypes
+        sc = self.sc
+        rows = torch.empty(gsel.numel(), HALO_COLS, dtype=torch.float64,
+                           device=sc.device)
+        if gsel.numel():
+            _lib.check(sc.lib.rbx_halo_pack(
+                ctypes.byref(sc.scene), gsel.data_ptr(), int(gsel.numel()),
+                rows.data_ptr(), 1, sc.stream), 'rbx_halo_pack')
+        return rows
 
     def _unpack(self, got, nr):
         P = self.sc.P
@@ -435,7 +443,7 @@ class SlabScene(object):
         if ns:
             _lib.check(sc.lib.rbx_halo_pack(
                 ctypes.byref(sc.scene), self._send_idx.data_ptr(), ns,
-                self._send_buf.data_ptr(), sc.stream), 'rbx_halo_pack')
+                self._send_buf.data_ptr(), 1, sc.stream), 'rbx_halo_pack')
         send = list(torch.split(self._send_buf, self._send_counts, 0))
         recv = list(torch.split(self._recv_buf, self._recv_counts, 0))
         self._p2p(send, recv, self._send_counts, self._recv_counts)
@@ -551,20 +559,15 @@ class SlabScene(object):
         sc = self.sc
         sc.push_touched()
         for k in range(nsteps):
-            sc.gtvf_kick(dt)
-            sc.gtvf_drift(dt)
-            sc.pose(_lib.POSE_POS | _lib.POSE_VEL | _lib.POSE_VEL_PREV |
-                    _lib.POSE_NORMALS)
+            # the fused step in two halves (two calls into the library), the
+            # halo exchange in between.  Particle velocities are formed where
+            # they are needed (RBX_PARAM_BODY_VEL; rbx_halo_pack does the
+            # same for the payload); u, v, w and the boundary normals are
+            # written by the last step of a batch only, as in
+            # DeviceScene.gtvf_step
+            p = sc.params(dt)
+            sc._gtvf_step_call(p, flags=2, evaluated=False)
             self.exchange_halo(full=self.lists_need_rebuild())
-            sc.cells_build()
-            sc.contact(dt)
-            sc.reduce_bodies()
-            sc.gtvf_kick(dt)
-            # the stage-3 particle velocities of a step are overwritten by
-            # stage 1 of the next one before anything reads them (the halo
-            # payload is packed after stage 1): only the last step of a
-            # batch writes them, as in DeviceScene.gtvf_step
-            if k == nsteps - 1:
-                sc.pose(_lib.POSE_VEL)
+            sc._gtvf_step_call(p, flags=4 | (0 if k == nsteps - 1 else 1))
         sc.steps_done += nsteps
         sc.mark_device_newer()
