@@ -422,6 +422,19 @@ int rbx_boundary_identify(const RbxPoints *pts, const RbxCells *cells, int dim,
                           const double *rho, double *normal_tmp,
                           double *normal, int32_t *is_boundary, void *stream);
 
+/* Setup path (one-off): set_total_mass, set_center_of_mass,
+ * set_moment_of_inertia_izz, set_moment_of_inertia_and_its_inverse and
+ * set_body_frame_position_vectors (rigid_body_common.py:21-107) of one rigid
+ * array whose particles are grouped by body: body b owns the particles
+ * [body_start[b], body_start[b + 1]).  Writes total_mass[nb], xcm[3 nb],
+ * izz[nb] (may be NULL), the inertia tensor about the centre of mass and its
+ * inverse [9 nb] (body frame = global frame at t = 0), dx0, dy0, dz0[n].    */
+int rbx_setup_bodies(int32_t n_bodies, const int32_t *body_start,
+                     const double *x, const double *y, const double *z,
+                     const double *m, double *total_mass, double *xcm,
+                     double *izz, double *inertia, double *inertia_inverse,
+                     double *dx0, double *dy0, double *dz0, void *stream);
+
 /* Whole GTVF step [upstream GTVFIntegrator.one_timestep, SURVEY App. C-6]:
  * kick, drift, pose, cells_build, contact, reduce, kick, velocities.
  * `src` = the source points (contact_force_is_boundary == 1) to bin.

@@ -285,57 +285,94 @@ DEM_STATE = ['x', 'y', 'z', 'u', 'v', 'w', 'wx', 'wy', 'wz', 'fx', 'fy', 'fz',
              'tng_y', 'tng_z', 'total_tng_contacts']
 
 
-def run_dem_case():
+def run_dem_case(dim=2):
     """DEMScheme (dem.py:628-828): LVCDisplacement + tangential-contact
     bookkeeping + DEMStep under GTVF sequencing.  No script of the reference
     instantiates the scheme; the constants it needs but does not create
     (kn, kt, alpha, mu by source dem_id, max_tng_contacts_limit, moi) are
-    added here."""
+    added here.  dim = 3: a 4 x 3 x 3 block of spheres on a
+    floor of spheres, velocities and spins about all three axes."""
     from pysph.base.kernels import CubicSpline
-    rng = np.random.default_rng(3)
+    rng = np.random.default_rng(3 if dim == 2 else 5)
     rad = 0.01
-    nx, ny = 6, 5
-    gx, gy = np.meshgrid(np.arange(nx), np.arange(ny), indexing='ij')
-    x = gx.ravel() * 1.98 * rad + rng.uniform(-0.02, 0.02, nx * ny) * rad
-    y = gy.ravel() * 1.97 * rad + rad * 0.99 + \
-        rng.uniform(-0.02, 0.02, nx * ny) * rad
-    n = x.size
-    m = 2500. * np.pi * rad**2
-    sand = get_particle_array(name='sand', x=x, y=y, h=1.2 * rad, m=m,
+    name = 'dem%dd' % dim
+    if dim == 2:
+        nx, ny = 6, 5
+        gx, gy = np.meshgrid(np.arange(nx), np.arange(ny), indexing='ij')
+        n = gx.size
+        x = gx.ravel() * 1.98 * rad + rng.uniform(-0.02, 0.02, n) * rad
+        y = gy.ravel() * 1.97 * rad + rad * 0.99 + \
+            rng.uniform(-0.02, 0.02, n) * rad
+        z = np.zeros(n)
+        m = 2500. * np.pi * rad**2
+        moi = 0.5 * m * rad**2
+    else:
+        gx, gy, gz = np.meshgrid(np.arange(4), np.arange(3), np.arange(3),
+                                 indexing='ij')
+        n = gx.size
+        x = gx.ravel() * 1.98 * rad + rng.uniform(-0.02, 0.02, n) * rad
+        y = gy.ravel() * 1.97 * rad + rad * 0.99 + \
+            rng.uniform(-0.02, 0.02, n) * rad
+        z = gz.ravel() * 1.98 * rad + rng.uniform(-0.02, 0.02, n) * rad
+        m = 2500. * 4. / 3. * np.pi * rad**3
+        moi = 0.4 * m * rad**2
+    sand = get_particle_array(name='sand', x=x, y=y, z=z, h=1.2 * rad, m=m,
                               rho=2500., rad_s=rad,
                               u=rng.uniform(-0.05, 0.05, n),
                               v=rng.uniform(-0.05, 0.05, n))
+    if dim == 3:
+        sand.w[:] = rng.uniform(-0.05, 0.05, n)
     sand.add_property('dem_id', type='int', data=0)
-    sand.add_property('moi', data=0.5 * m * rad**2)
+    sand.add_property('moi', data=moi)
     # quirk Q13 (dem.py:239-242): initialize_pair indexes the SOURCE array's
     # dem_id with an index recorded against another array; keep every array
     # at least as long as the longest one so that read stays in bounds
-    xw = (np.arange(n + 6) - 14) * 2 * rad
-    wall = get_particle_array(name='wall', x=xw, y=np.zeros_like(xw) - rad,
-                              h=1.2 * rad, m=m, rho=2500., rad_s=rad)
+    if dim == 2:
+        xw = (np.arange(n + 6) - 14) * 2 * rad
+        yw = np.zeros_like(xw) - rad
+        zw = np.zeros_like(xw)
+    else:
+        fi, fk = np.meshgrid(np.arange(-2, 6), np.arange(-2, 5),
+                             indexing='ij')
+        xw = fi.ravel() * 2. * rad
+        zw = fk.ravel() * 2. * rad
+        yw = np.zeros_like(xw) - rad
+        # ... and the floor particles that can touch the block come first, so
+        # that their indices also index the (shorter) sand array
+        near = np.argsort((xw - x.mean())**2 + (zw - z.mean())**2,
+                          kind='stable')
+        xw, zw = xw[near], zw[near]
+        assert xw.size >= n
+    wall = get_particle_array(name='wall', x=xw, y=yw, z=zw, h=1.2 * rad,
+                              m=m, rho=2500., rad_s=rad)
     wall.add_property('dem_id', type='int', data=1)
     for pa in (sand, wall):
         for p in ('wx', 'wy', 'wz'):
             pa.add_property(p)
     sand.wz[:] = rng.uniform(-5, 5, n)
-    sand.add_constant('max_tng_contacts_limit', 8)
+    if dim == 3:
+        sand.wx[:] = rng.uniform(-5, 5, n)
+        sand.wy[:] = rng.uniform(-5, 5, n)
+    limit = 8 if dim == 2 else 12
+    sand.add_constant('max_tng_contacts_limit', limit)
     sand.add_constant('kn', [1e5, 2e5])
     sand.add_constant('kt', [2. / 7. * 1e5, 2. / 7. * 2e5])
     sand.add_constant('alpha', [40., 60.])
     sand.add_constant('mu', [0.5, 0.3])
-    s = dem.DEMScheme(['sand'], ['wall'], dim=2, gy=-9.81)
+    s = dem.DEMScheme(['sand'], ['wall'], dim=dim, gy=-9.81)
     s.setup_properties([sand, wall])
     eqs = s.get_equations()
     st = {'sand': dem.DEMStep()}
-    kernel = CubicSpline(dim=2)
+    kernel = CubicSpline(dim=dim)
     arrays = [sand, wall]
     dt = 2e-5
-    nsteps, save = 60, (1, 2, 5, 10, 30, 60)
-    meta = {'name': 'dem2d', 'granular': ['sand'], 'boundaries': ['wall'],
-            'dim': 2, 'dt': dt, 'gx': 0., 'gy': -9.81, 'gz': 0.,
-            'nsteps': nsteps, 'save_steps': list(save),
+    nsteps, save = (60, (1, 2, 5, 10, 30, 60)) if dim == 2 else \
+        (30, (1, 2, 5, 10, 30))
+    meta = {'name': name, 'granular': ['sand'], 'boundaries': ['wall'],
+            'dim': dim, 'dt': dt, 'gx': 0., 'gy': -9.81, 'gz': 0.,
+            'nsteps': nsteps, 'save_steps': list(save), 'limit': limit,
             'radius_scale': kernel.radius_scale}
-    dump(os.path.join(GOLDEN, 'dem2d_scene.npz'), arrays, {'t': 0.0},
+    dump(os.path.join(GOLDEN, name + '_scene.npz'), arrays, {'t': 0.0},
          detailed_output=True, compress=True)
     out = {}
     t0 = time.time()
@@ -347,9 +384,9 @@ def run_dem_case():
                     sand.properties[nme].copy()
     meta['seconds'] = time.time() - t0
     out['__meta__'] = np.array(json.dumps(meta))
-    np.savez_compressed(os.path.join(GOLDEN, 'dem2d_ref.npz'), **out)
+    np.savez_compressed(os.path.join(GOLDEN, name + '_ref.npz'), **out)
     print('%-16s %4d steps %6.1fs  contacts %d' % (
-        'dem2d', nsteps, meta['seconds'], sand.total_tng_contacts.sum()))
+        name, nsteps, meta['seconds'], sand.total_tng_contacts.sum()))
 
 
 def run_canelas_case():
@@ -457,12 +494,15 @@ CASES = {
 
 if __name__ == '__main__':
     os.makedirs(GOLDEN, exist_ok=True)
-    which = sys.argv[1:] or list(CASES) + ['known', 'dem2d', 'canelas2d']
+    which = sys.argv[1:] or list(CASES) + ['known', 'dem2d', 'dem3d',
+                                           'canelas2d']
     for name in which:
         if name == 'known':
             known_answers()
         elif name == 'dem2d':
-            run_dem_case()
+            run_dem_case(2)
+        elif name == 'dem3d':
+            run_dem_case(3)
         elif name == 'canelas2d':
             run_canelas_case()
         else:

@@ -111,7 +111,7 @@ SYMBOLS = ['rbx_version', 'rbx_strerror', 'rbx_sizeof',
            'rbx_halo_pack', 'rbx_static_update',
            'rbx_halo_unpack', 'rbx_rk2_stage',
            'rbx_gtvf_step', 'rbx_contact_lvc', 'rbx_dem_step',
-           'rbx_boundary_identify']
+           'rbx_boundary_identify', 'rbx_setup_bodies']
 
 _lib = None
 
@@ -176,6 +176,7 @@ def load():
     L.rbx_boundary_identify.argtypes = [P(RbxPoints), P(RbxCells),
                                         ctypes.c_int, c_f64, c_vp, c_vp, c_vp,
                                         c_vp, c_vp, c_vp]
+    L.rbx_setup_bodies.argtypes = [c_i32] + [c_vp] * 14
     for i, cls in enumerate([RbxGridInfo, RbxPoints, RbxCells, RbxScene,
                              RbxParams, RbxDiag, RbxDemScene, RbxCanelas]):
         if L.rbx_sizeof(i) != ctypes.sizeof(cls):

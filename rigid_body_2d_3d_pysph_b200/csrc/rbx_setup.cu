@@ -128,7 +128,76 @@ int launch_all(const RbxPoints *pts, const RbxCells *cells, double rs, const dou
   return RBX_OK;
 }
 
+// set_total_mass, set_center_of_mass, set_moment_of_inertia_izz,
+// set_moment_of_inertia_and_its_inverse, set_body_frame_position_vectors
+// (rigid_body_common.py:21-107): one warp per body over its particles
+// [start[b], start[b + 1]), two passes (mass and centre of mass, then the
+// tensor about it), fixed shuffle trees; the 3x3 inverse by cofactors on lane
+// 0 (the reference calls np.linalg.inv: LU, same result to rounding; a
+// singular tensor gives inf / nan there and here).
+__global__ void __launch_bounds__(128)
+k_setup_bodies(int nb, const int32_t *start, const double *x, const double *y, const double *z,
+               const double *m, double *total_mass, double *xcm, double *izz, double *I_out,
+               double *Iinv_out, double *dx0, double *dy0, double *dz0) {
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (b >= nb) return;
+  const int q0 = start[b], q1 = start[b + 1];
+  double M = 0., sx = 0., sy = 0., sz = 0.;
+  for (int q = q0 + lane; q < q1; q += 32) {
+    const double mq = m[q];
+    M += mq; sx += mq * x[q]; sy += mq * y[q]; sz += mq * z[q];
+  }
+  M = rbx_warp_sum(M); sx = rbx_warp_sum(sx); sy = rbx_warp_sum(sy); sz = rbx_warp_sum(sz);
+  const double cx = sx / M, cy = sy / M, cz = sz / M;
+  double ixx = 0., iyy = 0., izz_ = 0., ixy = 0., ixz = 0., iyz = 0.;
+  for (int q = q0 + lane; q < q1; q += 32) {
+    const double mq = m[q];
+    const double dx = x[q] - cx, dy = y[q] - cy, dz = z[q] - cz;
+    dx0[q] = dx; dy0[q] = dy; dz0[q] = dz;
+    ixx += mq * (dy * dy + dz * dz);
+    iyy += mq * (dx * dx + dz * dz);
+    izz_ += mq * (dx * dx + dy * dy);
+    ixy += mq * dx * dy; ixz += mq * dx * dz; iyz += mq * dy * dz;
+  }
+  ixx = rbx_warp_sum(ixx); iyy = rbx_warp_sum(iyy); izz_ = rbx_warp_sum(izz_);
+  ixy = rbx_warp_sum(ixy); ixz = rbx_warp_sum(ixz); iyz = rbx_warp_sum(iyz);
+  if (lane == 0) {
+    total_mass[b] = M;
+    xcm[3 * b] = cx; xcm[3 * b + 1] = cy; xcm[3 * b + 2] = cz;
+    if (izz) izz[b] = izz_;
+    const double I[9] = {ixx, -ixy, -ixz, -ixy, iyy, -iyz, -ixz, -iyz, izz_};
+    for (int k = 0; k < 9; k++) I_out[9 * b + k] = I[k];
+    const double c00 = I[4] * I[8] - I[5] * I[7], c01 = I[5] * I[6] - I[3] * I[8],
+                 c02 = I[3] * I[7] - I[4] * I[6];
+    const double det = I[0] * c00 + I[1] * c01 + I[2] * c02;
+    const double inv[9] = {c00 / det, (I[2] * I[7] - I[1] * I[8]) / det,
+                           (I[1] * I[5] - I[2] * I[4]) / det,
+                           c01 / det, (I[0] * I[8] - I[2] * I[6]) / det,
+                           (I[2] * I[3] - I[0] * I[5]) / det,
+                           c02 / det, (I[1] * I[6] - I[0] * I[7]) / det,
+                           (I[0] * I[4] - I[1] * I[3]) / det};
+    for (int k = 0; k < 9; k++) Iinv_out[9 * b + k] = inv[k];
+  }
+}
+
 }  // namespace
+
+extern "C" int rbx_setup_bodies(int32_t n_bodies, const int32_t *body_start, const double *x,
+                                const double *y, const double *z, const double *m,
+                                double *total_mass, double *xcm, double *izz, double *inertia,
+                                double *inertia_inverse, double *dx0, double *dy0, double *dz0,
+                                void *stream) {
+  if (n_bodies < 0 || !body_start || !x || !y || !z || !m || !total_mass || !xcm || !inertia ||
+      !inertia_inverse || !dx0 || !dy0 || !dz0)
+    return RBX_ERR_INVALID;
+  if (n_bodies == 0) return RBX_OK;
+  k_setup_bodies<<<rbx_blocks((long long)n_bodies * 32, 128), 128, 0, (cudaStream_t)stream>>>(
+      n_bodies, body_start, x, y, z, m, total_mass, xcm, izz, inertia, inertia_inverse, dx0, dy0,
+      dz0);
+  RBX_CHECK_LAUNCH();
+  return RBX_OK;
+}
 
 extern "C" int rbx_boundary_identify(const RbxPoints *pts, const RbxCells *cells, int dim,
                                      double radius_scale, const double *m, const double *rho,

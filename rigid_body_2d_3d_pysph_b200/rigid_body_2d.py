@@ -29,5 +29,7 @@ class RigidBody2DScheme(RigidBody3DScheme):
             print("#============simulate problems other than 2 dimensions"
                   "============#")
 
+    _inertia_tensor = False
+
     def _set_inertia(self, pa):
         set_moment_of_inertia_izz(pa)

@@ -196,10 +196,14 @@ class RigidBody3DScheme(Scheme):
         pa.add_constant('max_dem_id', int(np.max(pa.dem_id)))
         if nb * tnb <= DENSE_SLOT_LIMIT:
             pa.add_constant('eta', np.zeros(nb * tnb))
-        set_total_mass(pa)
-        set_center_of_mass(pa)
-        self._set_inertia(pa)
-        set_body_frame_position_vectors(pa)
+        if self.device_setup:
+            from .setup_device import setup_rigid_bodies
+            setup_rigid_bodies(pa, tensor=self._inertia_tensor)
+        else:
+            set_total_mass(pa)
+            set_center_of_mass(pa)
+            self._set_inertia(pa)
+            set_body_frame_position_vectors(pa)
         if is_boundary is None:
             self._identify_boundary(pa)
         else:
@@ -212,11 +216,14 @@ class RigidBody3DScheme(Scheme):
                               'normal', 'is_boundary', 'fz', 'm',
                               'body_id', 'h'])
 
+    _inertia_tensor = True      # (the 2-D scheme sets izz only)
+
     def _set_inertia(self, pa):
         set_moment_of_inertia_and_its_inverse(pa)
 
-    # device_setup = True routes the boundary identification through the CUDA
-    # cell list (setup_device.py) instead of the host KD-tree evaluator
+    # device_setup = True routes the per-body setup (mass, centre of mass,
+    # inertia, body-frame vectors) and the boundary identification through
+    # setup_device.py (CUDA) instead of the host helpers
     device_setup = False
 
     def _identify_boundary(self, pa):

@@ -3,15 +3,18 @@ produced by the reference's own dem.py methods."""
 import numpy as np
 import pytest
 
-from tests.test_oracle_dem import DEM_STATE, canonical_history, load_dem
+from tests.test_oracle_dem import (DEM_CASES, DEM_STATE, canonical_history,
+                                   load_dem)
 from tests.util import assert_close
 
 pytestmark = pytest.mark.gpu
 
 
-def test_dem_gpu_matches_reference():
+@pytest.mark.parametrize('name', DEM_CASES)
+def test_dem_gpu_matches_reference(name):
     from rigid_body_2d_3d_pysph_b200.dem import DemDeviceScene
-    arrays, ref, meta = load_dem()
+    arrays, ref, meta = load_dem(name)
+    limit = meta['limit']
     sc = DemDeviceScene(arrays, meta['granular'], meta['boundaries'],
                         dim=meta['dim'], gx=meta['gx'], gy=meta['gy'],
                         gz=meta['gz'], radius_scale=meta['radius_scale'])
@@ -25,12 +28,13 @@ def test_dem_gpu_matches_reference():
         assert np.array_equal(sand.total_tng_contacts,
                               ref[pre + 'total_tng_contacts'])
         got = canonical_history(sand.tng_idx, sand.tng_idx_dem_id, sand.tng_x,
-                                sand.tng_y, sand.tng_z, 8)
+                                sand.tng_y, sand.tng_z, limit)
         want = canonical_history(*[ref[pre + n] for n in (
-            'tng_idx', 'tng_idx_dem_id', 'tng_x', 'tng_y', 'tng_z')], 8)
+            'tng_idx', 'tng_idx_dem_id', 'tng_x', 'tng_y', 'tng_z')], limit)
         assert np.array_equal(got[0], want[0]) and \
             np.array_equal(got[1], want[1]), step
-        tscale = max(np.abs(want[2]).max(), np.abs(want[3]).max(), 1e-12)
+        tscale = max(np.abs(want[2]).max(), np.abs(want[3]).max(),
+                     np.abs(want[4]).max(), 1e-12)
         for k in (2, 3, 4):
             assert_close(got[k], want[k], 1e-10, 'dem step %d tng[%d]' %
                          (step, k), tscale)

@@ -250,6 +250,46 @@ def test_device_boundary_identification_equals_host():
             assert np.abs(host.normal - dev.normal).max() < 1e-10
 
 
+def test_device_body_setup_equals_host():
+    """total mass, centre of mass, izz, inertia tensor and
+    inverse, body-frame vectors from the device (rbx_setup_bodies) equal the
+    host helpers (rigid_body_common.py:21-107) to rounding, on the six cubes
+    of benchmark_5_3d, the 33 cylinders of stack_of_cylinders and a 2000-body
+    pile."""
+    from rigid_body_2d_3d_pysph_b200 import rigid_body_common as rc
+    from rigid_body_2d_3d_pysph_b200.scenes import synthetic_pile
+    from rigid_body_2d_3d_pysph_b200.setup_device import setup_rigid_bodies
+    from tests.util import load_config
+    cases = [load_config('benchmark_5_3d')[0][0],
+             load_config('stack_of_cylinders')[0][0],
+             synthetic_pile(2000)[0][0]]
+    names = ['total_mass', 'xcm', 'izz', 'inertia_tensor_body_frame',
+             'inertia_tensor_inverse_body_frame',
+             'inertia_tensor_global_frame',
+             'inertia_tensor_inverse_global_frame']
+    for k, pa in enumerate(cases):
+        planar = k == 1                  # cylinders: singular 3-D tensor
+        host, dev = _clone([pa])[0], _clone([pa])[0]
+        for q in (host, dev):
+            for n in names:
+                q.constants[n][:] = 0.
+            q.dx0[:] = 0.
+        rc.set_total_mass(host)
+        rc.set_center_of_mass(host)
+        rc.set_moment_of_inertia_izz(host)
+        if not planar:
+            rc.set_moment_of_inertia_and_its_inverse(host)
+        rc.set_body_frame_position_vectors(host)
+        setup_rigid_bodies(dev, tensor=not planar)
+        for n in names:
+            a, b = host.constants[n], dev.constants[n]
+            assert np.abs(a - b).max() <= 1e-11 * max(np.abs(a).max(), 1e-300), \
+                (k, n, np.abs(a - b).max())
+        for n in ('dx0', 'dy0', 'dz0'):
+            assert np.abs(host.properties[n] - dev.properties[n]).max() < 1e-14
+        assert host.total_mass.min() > 0 and np.abs(host.xcm).max() > 0
+
+
 def test_neighbour_list_structures():
     """The data structures between the three contact kernels, on configs 3
     and 4: nbr_pos lists grouped by source body with the first entry of a

@@ -3,6 +3,7 @@ import json
 import os
 
 import numpy as np
+import pytest
 
 from oracle import rbo
 from rigid_body_2d_3d_pysph_b200.compat.output import load_scene
@@ -27,15 +28,21 @@ def canonical_history(idx, dem, tx, ty, tz, limit):
     return [np.take_along_axis(a, order, 1) for a in out]
 
 
-def load_dem():
-    arrays, _ = load_scene(os.path.join(GOLDEN, 'dem2d_scene.npz'))
-    ref = np.load(os.path.join(GOLDEN, 'dem2d_ref.npz'))
+DEM_CASES = ['dem2d', 'dem3d']
+
+
+def load_dem(name='dem2d'):
+    arrays, _ = load_scene(os.path.join(GOLDEN, name + '_scene.npz'))
+    ref = np.load(os.path.join(GOLDEN, name + '_ref.npz'))
     meta = json.loads(str(ref['__meta__']))
+    meta.setdefault('limit', 8)
     return arrays, ref, meta
 
 
-def test_dem_oracle_matches_reference():
-    arrays, ref, meta = load_dem()
+@pytest.mark.parametrize('name', DEM_CASES)
+def test_dem_oracle_matches_reference(name):
+    arrays, ref, meta = load_dem(name)
+    limit = meta['limit']
     p = rbo.make_params(meta['dim'], meta['dt'], gx=meta['gx'], gy=meta['gy'],
                         gz=meta['gz'], radius_scale=meta['radius_scale'])
     sand = arrays[0]
@@ -47,15 +54,16 @@ def test_dem_oracle_matches_reference():
         assert np.array_equal(sand.total_tng_contacts,
                               ref[pre + 'total_tng_contacts'])
         got = canonical_history(sand.tng_idx, sand.tng_idx_dem_id, sand.tng_x,
-                                sand.tng_y, sand.tng_z, 8)
+                                sand.tng_y, sand.tng_z, limit)
         want = canonical_history(*[ref[pre + n] for n in (
-            'tng_idx', 'tng_idx_dem_id', 'tng_x', 'tng_y', 'tng_z')], 8)
+            'tng_idx', 'tng_idx_dem_id', 'tng_x', 'tng_y', 'tng_z')], limit)
         assert np.array_equal(got[0], want[0]) and \
             np.array_equal(got[1], want[1]), step
-        tscale = max(np.abs(want[2]).max(), np.abs(want[3]).max(), 1e-12)
+        tscale = max(np.abs(want[2]).max(), np.abs(want[3]).max(),
+                     np.abs(want[4]).max(), 1e-12)
         for k in (2, 3, 4):
-            assert_close(got[k], want[k], 1e-10, 'dem2d step %d tng[%d]' %
-                         (step, k), tscale)
+            assert_close(got[k], want[k], 1e-10, '%s step %d tng[%d]' %
+                         (name, step, k), tscale)
         fs = np.abs(ref[pre + 'fx']).max() + np.abs(ref[pre + 'fy']).max()
         for n in DEM_STATE:
             if n.startswith('tng'):
@@ -64,5 +72,5 @@ def test_dem_oracle_matches_reference():
             if n.startswith('tor'):
                 scale = fs * 0.01
             assert_close(getattr(sand, n), ref[pre + n], 1e-10,
-                         'dem2d step %d %s' % (step, n), scale)
+                         '%s step %d %s' % (name, step, n), scale)
     assert sand.total_tng_contacts.sum() > 50
