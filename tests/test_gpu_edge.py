@@ -285,8 +285,12 @@ def test_device_body_setup_equals_host():
             a, b = host.constants[n], dev.constants[n]
             assert np.abs(a - b).max() <= 1e-11 * max(np.abs(a).max(), 1e-300), \
                 (k, n, np.abs(a - b).max())
+        # (the centre of mass rounds at 1e-16 of the coordinates)
+        scale = max(np.abs(pa.x).max(), np.abs(pa.y).max(),
+                    np.abs(pa.z).max(), 1.)
         for n in ('dx0', 'dy0', 'dz0'):
-            assert np.abs(host.properties[n] - dev.properties[n]).max() < 1e-14
+            assert np.abs(host.properties[n] -
+                          dev.properties[n]).max() < 1e-14 * scale
         assert host.total_mass.min() > 0 and np.abs(host.xcm).max() > 0
 
 
