@@ -248,6 +248,7 @@ class SlabScene(object):
         self.bytes_recv = 0
         self.migrations = 0
         self.bodies_moved = 0
+        self._flag_host = self._flag_event = None
         self._bind(scene)
 
     def _bind(self, scene):
@@ -450,8 +451,12 @@ class SlabScene(object):
         if nr:
             _lib.check(sc.lib.rbx_halo_unpack(
                 ctypes.byref(sc.scene), self.halo_off, nr,
-                self._recv_buf.data_ptr(), sc.skin, sc.stream),
+                self._recv_buf.data_ptr(), 1e300, sc.stream),
                 'rbx_halo_unpack')
+            # (no receiver-side displacement check, skin = inf: the rebuild
+            # decision is global and the OWNER of these particles raises
+            # the flag -- its per-body bound is never smaller than the
+            # displacement of a particle -- before the all-reduce)
         self.bytes_sent += ns * HALO_COLS * 8
         self.bytes_recv += nr * HALO_COLS * 8
 
@@ -567,7 +572,26 @@ class SlabScene(object):
             # DeviceScene.gtvf_step
             p = sc.params(dt)
             sc._gtvf_step_call(p, flags=2, evaluated=False)
-            self.exchange_halo(full=self.lists_need_rebuild())
+            # The rebuild decision is global (all_reduce MAX of the device
+            # flag) and the host has to know it: it picks between the halo
+            # refresh and a full exchange.  The refresh is right nine times
+            # out of ten, so it is issued BEFORE the host reads the flag --
+            # the device packs, sends and unpacks while the flag travels --
+            # and a full exchange follows only if the flag says so (it
+            # replaces what the refresh wrote).
+            if self.world > 1:
+                self._all_reduce_max(sc.rebuild)
+            if self._flag_host is None:
+                self._flag_host = torch.zeros(1, dtype=sc.rebuild.dtype
+                                              ).pin_memory()
+                self._flag_event = torch.cuda.Event()
+            self._flag_host.copy_(sc.rebuild, non_blocking=True)
+            self._flag_event.record(torch.cuda.current_stream(sc.device))
+            if self._send_idx is not None:
+                self._refresh_halo()
+            self._flag_event.synchronize()
+            if self._send_idx is None or int(self._flag_host[0]) != 0:
+                self.exchange_halo(full=True)
             sc._gtvf_step_call(p, flags=4 | (0 if k == nsteps - 1 else 1))
         sc.steps_done += nsteps
         sc.mark_device_newer()
