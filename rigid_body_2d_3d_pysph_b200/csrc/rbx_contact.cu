@@ -1104,8 +1104,9 @@ k_slots(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
 //   dB = sqrt3 (ex w + L dw),   cu = (list_cap + 16) u  (accumulation).
 // No contact is certain when
 //   A.B - [w dB + L w dA + dA dB] > spacing0 (|A| + dA) (w + dw)
-// (|A| <= w, |B| <= L w), tested on squares; NaN (coincident points) fails the
-// test and is kept.  Runs past ordinal 30 share mask bit 31.
+// (|A| <= w, |B| <= L w; |A| + dA is taken as the root of |A|^2 + dA (2 w +
+// dA), MUFU.SQRT within the 1e-4 allowance on spacing0); NaN (coincident
+// points) fails the test and is kept.  Runs past ordinal 30 share mask bit 31.
 #ifndef RBX_FILTER_MINB
 #define RBX_FILTER_MINB 32
 #endif
@@ -1151,7 +1152,7 @@ k_filter(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P
       const float ex = 2.1f * kU * E;
       const float er = kSqrt3 * ex + 4.f * kU * Lr;
       const float eu = ex + er;
-      const float s0sq = s0 * s0 * 1.0001f;
+      const float s0f = s0 * 1.0001f;
       // uniform h: constants of the kernel
       float h1 = 0.f, Th = 0.f, T = 0.f, dfloor = 0.f;
       if (UNIFORM_H) {
@@ -1205,9 +1206,15 @@ k_filter(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P
           const float lhs = ab - eab;
           const float aahi = fmaf(dA, fmaf(2.f, w1, dA), aa);
           const float wh = w1 + dw;
-          const float rhs = s0sq * (wh * wh) * aahi;
+          // (not on squares: for a slot of a few entries at the edge of the
+          // support w is 1e-12 .. 1e-11, A.B is 1e-25 and its square
+          // underflows FP32 -- such slots, 60 % of what this pass used to
+          // keep, could not be dropped although they are 3 spacings away)
+          float sq;
+          asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(aahi));
+          const float rhs = s0f * wh * sq;
           // w <= 1e-12: the slot has no normal, dist = 0, overlap == spacing0
-          const bool drop = (wh < 0.99e-12f) || (lhs > 0.f && lhs * lhs > rhs);
+          const bool drop = (wh < 0.99e-12f) || (lhs > 0.f && lhs > rhs);
           if (!drop || all) {
             // the exact pass starts at the first kept run and stops after
             // the last one
