@@ -1118,6 +1118,12 @@ k_filter(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P
   const int lane = threadIdx.x;
   const size_t n_rigid = (size_t)S.n_rigid;
   const float4 *__restrict__ pos = reinterpret_cast<const float4 *>(S.pos32);
+  // list entry -> position: the byte offset q * 16 in 32 bits (the shift drops
+  // the run marker in bit 31; n_total < 2^28, checked by the caller)
+  const char *__restrict__ posb = reinterpret_cast<const char *>(S.pos32);
+  auto gather = [&](int q) -> float4 {
+    return *reinterpret_cast<const float4 *>(posb + ((unsigned)q << 4));
+  };
   const int nitems = (S.n_rigid + 31) / 32;
   unsigned npairs = 0;
   const bool dense_out = !S.alist_out || (P.flags & RBX_PARAM_DENSE_OUT);
@@ -1237,9 +1243,9 @@ k_filter(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P
       int la = nlist > 2 ? cl[2 * n_rigid] : 0;
       int lb = nlist > 3 ? cl[3 * n_rigid] : 0;
       cl += 4 * n_rigid;
-      float4 sa = pos[(unsigned)qa & 0x7fffffffu], sb = pos[(unsigned)qb & 0x7fffffffu];
+      float4 sa = gather(qa), sb = gather(qb);
       for (int e0 = 0; e0 < nlist; e0 += 2) {
-        const float4 ga = pos[(unsigned)la & 0x7fffffffu], gb = pos[(unsigned)lb & 0x7fffffffu];
+        const float4 ga = gather(la), gb = gather(lb);
         const int na = (e0 + 4 < nlist) ? cl[0] : 0;
         const int nb = (e0 + 5 < nlist) ? cl[n_rigid] : 0;
         cl += 2 * n_rigid;
@@ -1376,7 +1382,8 @@ extern "C" int rbx_contact_slots(const RbxScene *scene, const RbxCells *cells,
   // two-precision evaluation unless the caller asks for the one-pass FP64
   // evaluation, wants per-slot diagnostics, or has no FP32 positions
   const bool fast = scene->pos32 && scene->clist && !(params->flags & RBX_PARAM_EXACT) &&
-                    !d.key && !d.pairs && scene->list_cap < (1 << 20);
+                    !d.key && !d.pairs && scene->list_cap < (1 << 20) &&
+                    scene->n_total < (1 << 28);
   // all CTAs resident at once (RBX_SLOTS_MINB per SM), odd count
   int ng = rbx_blocks(scene->n_rigid, kSlotsCta);
   const int resident = sms * RBX_SLOTS_MINB - 1;
