@@ -530,6 +530,8 @@ class DeviceScene(object):
         return None
 
     def pull(self, pa, name):
+        if name in ('u', 'v', 'w', 'normal'):
+            self.finalize_particles()
         t = self._slice(pa, name)
         if t is None:
             return
@@ -608,6 +610,7 @@ class DeviceScene(object):
             self.stream), 'rbx_cells_build')
 
     def contact(self, dt, diag=None):
+        self.finalize_particles()      # the unfused op reads u, v, w
         p = self.params(dt)
         _lib.check(self.lib.rbx_contact_mofidi(
             ctypes.byref(self.scene), ctypes.byref(self._cells),
@@ -623,6 +626,7 @@ class DeviceScene(object):
         array needs the property ``rad_s`` and the constants ``E`` and
         ``poisson_ratio``.  Follow with ``reduce_bodies()``."""
         self.push_touched()
+        self.finalize_particles()
         if getattr(self, '_canelas', None) is None:
             f64, i32 = torch.float64, torch.int32
             for pa in self.arrays:
@@ -699,6 +703,8 @@ class DeviceScene(object):
                    'drift')
 
     def pose(self, flags):
+        if flags & _lib.POSE_VEL:
+            self._particles_stale = False
         _lib.check(self.lib.rbx_pose_particles(ctypes.byref(self.scene),
                                                int(flags), self.stream),
                    'pose')
@@ -723,19 +729,31 @@ class DeviceScene(object):
         # of the next one before anything reads them, and the boundary
         # normals are a function of R alone: inside a batch only the last
         # step writes them (flag bit 0 of rbx_gtvf_step).
+        # They are not even written by the last step: whoever looks at u, v,
+        # w or the normals first -- a pull to the host, an unfused op -- gets
+        # them from finalize_particles().  An application that steps one
+        # step at a time and reads per-body results only never pays for them.
         left = nsteps
         while left and self._dense_pending:     # never captured in a graph
-            self._gtvf_step_call(self.params(dt), flags=0 if left == 1 else 1)
+            self._gtvf_step_call(self.params(dt), flags=1)
             left -= 1
         p = self.params(dt)
         if graph and left >= 4:
             self._run_graph(p, left)
-            self.pose(_lib.POSE_VEL | _lib.POSE_NORMALS)
         else:
             for k in range(left):
-                self._gtvf_step_call(p, flags=0 if k == left - 1 else 1)
+                self._gtvf_step_call(p, flags=1)
+        if nsteps > 0:
+            self._particles_stale = True
         self.steps_done += nsteps
         self.mark_device_newer()
+
+    def finalize_particles(self):
+        """Stage-3 particle velocities and the rotated boundary normals of
+        the last fused step, if they have not been formed yet."""
+        if getattr(self, '_particles_stale', False):
+            self._particles_stale = False
+            self.pose(_lib.POSE_VEL | _lib.POSE_NORMALS)
 
     def _run_graph(self, p, nsteps):
         """Two steps (one history ping-pong period) captured as a CUDA graph:

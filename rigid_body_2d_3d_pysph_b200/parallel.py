@@ -568,8 +568,7 @@ class SlabScene(object):
             # halo exchange in between.  Particle velocities are formed where
             # they are needed (RBX_PARAM_BODY_VEL; rbx_halo_pack does the
             # same for the payload); u, v, w and the boundary normals are
-            # written by the last step of a batch only, as in
-            # DeviceScene.gtvf_step
+            # formed when somebody asks for them, as in DeviceScene.gtvf_step
             p = sc.params(dt)
             sc._gtvf_step_call(p, flags=2, evaluated=False)
             # The rebuild decision is global (all_reduce MAX of the device
@@ -592,6 +591,8 @@ class SlabScene(object):
             self._flag_event.synchronize()
             if self._send_idx is None or int(self._flag_host[0]) != 0:
                 self.exchange_halo(full=True)
-            sc._gtvf_step_call(p, flags=4 | (0 if k == nsteps - 1 else 1))
+            sc._gtvf_step_call(p, flags=4 | 1)
+        if nsteps > 0:
+            sc._particles_stale = True     # see DeviceScene.finalize_particles
         sc.steps_done += nsteps
         sc.mark_device_newer()

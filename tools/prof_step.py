@@ -17,7 +17,8 @@ settle = int(sys.argv[2]) if len(sys.argv) > 2 else 2000
 skin = float(sys.argv[3]) if len(sys.argv) > 3 else 0.05
 (body, wall), scheme, info = synthetic_pile(nb)
 sc = DeviceScene([body, wall], ['body'], ['wall'], dim=3, gy=-9.81,
-                 eta_uniform=info['eta_uniform'], skin_factor=skin)
+                 eta_uniform=info['eta_uniform'], skin_factor=skin,
+                 list_cap=int(os.environ.get('RBX_LIST_CAP', '96')))
 sc.gtvf_step(1e-4, settle, graph=True)
 torch.cuda.synchronize()
 sc.check_status()
