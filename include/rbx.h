@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RBX_VERSION 403 /* 0.4.3 */
+#define RBX_VERSION 404 /* 0.4.4 */
 
 typedef enum {
   RBX_OK = 0,
@@ -216,6 +216,13 @@ typedef struct {
    * rbx_halo_unpack raise `rebuild` when one of them has moved more than
    * skin / 2 since -- the rule the drift kernel applies to the bodies.       */
   double *static_ref;
+  /* A second stream of the caller's (a cudaStream_t), or NULL.  When
+   * rbx_gtvf_step is called while `stream` is being captured into a CUDA
+   * graph, the list rebuild (cell list + neighbour lists, ~13 kernels that
+   * otherwise all launch and return at once on the 9 steps of 10 that reuse
+   * the lists) is captured through it into the body of a conditional IF node
+   * on *rebuild: a step that reuses the lists then does not launch them.    */
+  void *aux_stream;
 } RbxScene;
 
 typedef struct {

@@ -66,7 +66,7 @@ class RbxScene(ctypes.Structure):
                [(n, c_vp) for n in ('alist_out', 'alist_prev', 'acount_out',
                                     'acount_prev', 'body_tag', 'aux32')] + \
                [('h_uniform', c_f64), ('gravity', c_f64 * 3),
-                ('static_ref', c_vp)]
+                ('static_ref', c_vp), ('aux_stream', c_vp)]
 
 
 _DEM_PTRS = ['x', 'y', 'z', 'u', 'v', 'w', 'wx', 'wy', 'wz', 'h', 'm', 'rad_s',

@@ -11,6 +11,7 @@
 //   RK2RigidBody3DStep                rigid_body_3d.py:406-575
 //   stage1/2/3 particle updates       rigid_body_3d.py:62-95, 134-169, 192-225
 #include "rbx_common.cuh"
+#include <string.h>
 
 namespace {
 
@@ -405,6 +406,68 @@ extern "C" int rbx_rk2_stage(const RbxScene *scene, int stage, double dt, int fi
 // Whole GTVF step: kick + drift (one body launch), positions + stage-1
 // velocities (one particle launch), cell list, contact, reduce + kick (one
 // body launch), stage-3 velocities.
+// ---- list rebuild, conditional inside a captured graph -----------------------
+__global__ void k_set_conditional(cudaGraphConditionalHandle h, const uint32_t *flag) {
+  cudaGraphSetConditional(h, *flag != 0u ? 1u : 0u);
+}
+
+static int rebuild_lists_plain(const RbxScene *scene, const RbxPoints *src, const RbxCells *cells,
+                               const RbxParams *par, void *ws, size_t ws_bytes, cudaStream_t st) {
+  int rc = rbx_cells_build(src, cells, par->reach, scene->status, ws, ws_bytes, st);
+  if (rc) return rc;
+  return rbx_contact_neighbours(scene, cells, par, st);
+}
+
+// Cell list + neighbour lists.  Every kernel of the rebuild returns at once
+// while *rebuild == 0, but 13 launches that do nothing still cost 80 us of a
+// 1.8 ms step.  When `st` is being captured and the caller gave a second
+// stream, the rebuild is captured into the body of a conditional IF node on
+// *rebuild instead (CUDA 12.4 graph conditionals): steps that reuse the lists
+// skip it on the device, without a host decision.
+static int rebuild_lists(const RbxScene *scene, const RbxPoints *src, const RbxCells *cells,
+                         const RbxParams *par, void *ws, size_t ws_bytes, cudaStream_t st) {
+  cudaStream_t aux = (cudaStream_t)scene->aux_stream;
+  if (aux && scene->rebuild && cells->cond == scene->rebuild && par->skin > 0.) {
+    cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
+    cudaGraph_t graph = nullptr;
+    const cudaGraphNode_t *deps = nullptr;
+    size_t ndeps = 0;
+    unsigned long long id = 0;
+    if (cudaStreamGetCaptureInfo_v2(st, &status, &id, &graph, &deps, &ndeps) == cudaSuccess &&
+        status == cudaStreamCaptureStatusActive && graph) {
+      cudaGraphConditionalHandle handle;
+      if (cudaGraphConditionalHandleCreate(&handle, graph, 0, cudaGraphCondAssignDefault) ==
+          cudaSuccess) {
+        k_set_conditional<<<1, 1, 0, st>>>(handle, scene->rebuild);
+        if (cudaStreamGetCaptureInfo_v2(st, &status, &id, &graph, &deps, &ndeps) != cudaSuccess)
+          return RBX_ERR_LAUNCH;
+        cudaGraphNodeParams np = {};
+        np.type = cudaGraphNodeTypeConditional;
+        np.conditional.handle = handle;
+        np.conditional.type = cudaGraphCondTypeIf;
+        np.conditional.size = 1;
+        cudaGraphNode_t node;
+        if (cudaGraphAddNode(&node, graph, deps, ndeps, &np) != cudaSuccess) return RBX_ERR_LAUNCH;
+        cudaGraph_t body = np.conditional.phGraph_out[0];
+        if (cudaStreamBeginCaptureToGraph(aux, body, nullptr, nullptr, 0,
+                                          cudaStreamCaptureModeRelaxed) != cudaSuccess)
+          return RBX_ERR_LAUNCH;
+        const int rc = rebuild_lists_plain(scene, src, cells, par, ws, ws_bytes, aux);
+        cudaGraph_t got = nullptr;
+        if (cudaStreamEndCapture(aux, &got) != cudaSuccess || rc) return rc ? rc : RBX_ERR_LAUNCH;
+        if (cudaStreamUpdateCaptureDependencies(st, &node, 1, cudaStreamSetCaptureDependencies) !=
+            cudaSuccess)
+          return RBX_ERR_LAUNCH;
+        return RBX_OK;
+      }
+      cudaGetLastError();      // no conditional nodes here: plain launches
+    } else {
+      cudaGetLastError();
+    }
+  }
+  return rebuild_lists_plain(scene, src, cells, par, ws, ws_bytes, st);
+}
+
 extern "C" int rbx_gtvf_step(const RbxScene *scene, const RbxPoints *src, const RbxCells *cells,
                              const RbxParams *params, void *workspace, size_t workspace_bytes,
                              int flags, void *stream) {
@@ -424,9 +487,8 @@ extern "C" int rbx_gtvf_step(const RbxScene *scene, const RbxPoints *src, const 
   if (post) {
     RbxParams par = *params;
     par.flags |= RBX_PARAM_BODY_VEL;
-    if ((rc = rbx_cells_build(src, cells, params->reach, scene->status, workspace,
-                              workspace_bytes, stream))) return rc;
-    if ((rc = rbx_contact_mofidi(scene, cells, &par, nullptr, stream))) return rc;
+    if ((rc = rebuild_lists(scene, src, cells, &par, workspace, workspace_bytes, st))) return rc;
+    if ((rc = rbx_contact_slots(scene, cells, &par, nullptr, stream))) return rc;
     // reduce (k_reduce, warp per body) and kick (k_bodies, thread per body)
     // are two launches: with the kick's divisions on lane 0 of every reduce
     // warp, the warp sat on its slot three times longer than its loads take

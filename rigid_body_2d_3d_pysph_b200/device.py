@@ -377,6 +377,10 @@ class DeviceScene(object):
         s.h_uniform = self.h_uniform
         s.body_tag, s.aux32 = _ptr(T['body_tag']), _ptr(T['aux32'])
         s.static_ref = _ptr(T['static_ref'])
+        # for the conditional list rebuild inside captured graphs
+        if getattr(self, '_aux_stream', None) is None:
+            self._aux_stream = torch.cuda.Stream(self.device)
+        s.aux_stream = self._aux_stream.cuda_stream
         for n in ['total_mass', 'izz', 'spacing0', 'xcm', 'vcm', 'ang_mom',
                   'omega', 'force', 'torque', 'R', 'R_prev', 'xcm0', 'vcm0',
                   'ang_mom0', 'R0']:

@@ -29,7 +29,7 @@ def test_header_symbols_exported():
 def test_struct_mirrors_match_library():
     _ensure_built()
     L = _lib.load()      # raises on any sizeof mismatch
-    assert L.rbx_version() == 403
+    assert L.rbx_version() == 404
     assert L.rbx_strerror(-2) == b'workspace too small'
 
 
