@@ -550,12 +550,18 @@ def main():
                    min(args.settle, args.cpu_settle), args.cpu_steps)}
 
     if rank == 0:
-        # k_bodies, k_pose, 8 cell-list kernels, k_neighbours, k_pos32,
-        # k_list_sort, k_list_commit, k_static_commit, k_list_clear,
-        # k_sparse_reset, k_filter, k_slots, k_reduce, k_bodies (memsets not
-        # counted; the cell-list and list kernels return at once on the
-        # steps that reuse the neighbour lists)
-        launches_per_step = 21
+        # every step: k_bodies, k_pose, k_sparse_reset, k_filter, k_slots x 2
+        # (one of them returns at once), k_reduce, k_bodies = 8; a list
+        # rebuild adds 8 cell-list kernels, k_neighbours, k_pos32, k_list_sort,
+        # k_list_commit, k_static_commit, k_list_clear = 14.  One GPU (CUDA
+        # graph): the rebuild is the body of a conditional node, launched
+        # only on the steps that rebuild, + k_set_conditional every step;
+        # N > 1 (eager): all 22 every step, the rebuild kernels returning at
+        # once on the steps that reuse the lists.  Memsets not counted.
+        if world == 1:
+            launches = args.steps * (9 + 14 * rebuilds_per_step)
+        else:
+            launches = args.steps * 22
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT,
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
@@ -586,7 +592,7 @@ def main():
             'candidate_tests_per_step': tot_cand / args.steps,
             'roofline': roof, 'step_roofline': step_roof,
             'cpu_baseline': cpu, 'e2e': e2e,
-            'gpu_launches': launches_per_step * args.steps,
+            'gpu_launches': int(round(launches)),
             'clocks': sampler.summary(),
             'scene_build_s': t_build,
         }

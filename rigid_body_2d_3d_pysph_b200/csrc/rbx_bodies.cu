@@ -11,6 +11,8 @@
 //   RK2RigidBody3DStep                rigid_body_3d.py:406-575
 //   stage1/2/3 particle updates       rigid_body_3d.py:62-95, 134-169, 192-225
 #include "rbx_common.cuh"
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace {
@@ -433,11 +435,17 @@ static int rebuild_lists(const RbxScene *scene, const RbxPoints *src, const RbxC
     const cudaGraphNode_t *deps = nullptr;
     size_t ndeps = 0;
     unsigned long long id = 0;
-    if (cudaStreamGetCaptureInfo_v2(st, &status, &id, &graph, &deps, &ndeps) == cudaSuccess &&
-        status == cudaStreamCaptureStatusActive && graph) {
+    const cudaError_t e1 = cudaStreamGetCaptureInfo_v2(st, &status, &id, &graph, &deps, &ndeps);
+    const bool dbg = getenv("RBX_DEBUG_GRAPH") != nullptr;
+    if (dbg) fprintf(stderr, "[rbx] capture info: err %d status %d graph %p deps %zu\n", (int)e1,
+                     (int)status, (void *)graph, ndeps);
+    if (e1 == cudaSuccess && status == cudaStreamCaptureStatusActive && graph) {
       cudaGraphConditionalHandle handle;
-      if (cudaGraphConditionalHandleCreate(&handle, graph, 0, cudaGraphCondAssignDefault) ==
-          cudaSuccess) {
+      const cudaError_t e2 =
+          cudaGraphConditionalHandleCreate(&handle, graph, 0, cudaGraphCondAssignDefault);
+      if (dbg) fprintf(stderr, "[rbx] conditional handle: err %d (%s)\n", (int)e2,
+                       cudaGetErrorString(e2));
+      if (e2 == cudaSuccess) {
         k_set_conditional<<<1, 1, 0, st>>>(handle, scene->rebuild);
         if (cudaStreamGetCaptureInfo_v2(st, &status, &id, &graph, &deps, &ndeps) != cudaSuccess)
           return RBX_ERR_LAUNCH;
