@@ -241,6 +241,7 @@ class SlabScene(object):
         self.rank, self.world, self.group = rank, world, group
         self.halo_name = halo_name
         self.staged = world > 1 and _staged(group)
+        self.use_graphs = True
         # ownership intervals [cuts[k], cuts[k+1]) along x; None until the
         # first migrate() (ownership = where the scene builder put the body)
         self.cuts = None if cuts is None else np.asarray(cuts, np.float64)
@@ -253,6 +254,7 @@ class SlabScene(object):
 
     def _bind(self, scene):
         self.sc = scene
+        self._graphs = {}
         halo_name = self.halo_name
         pas = dict((a.name, a) for a in scene.arrays)
         self.halo_off = scene.p_off[halo_name]
@@ -540,6 +542,37 @@ class SlabScene(object):
         self._bind(new_sc)
         return received
 
+    def _half(self, p, flags):
+        """One half of the fused step (rbx_gtvf_step flag bit 1: up to the
+        positions; bit 2: from the cell list on).  Each half is a fixed
+        sequence of launches with no host decision inside, so it is captured
+        once per history parity into a CUDA graph and replayed: one launch
+        instead of 2 / 20, and the list rebuild of the second half becomes
+        the body of a conditional node (see rbx_gtvf_step).  The halo
+        exchange and the host's rebuild decision stay between the two."""
+        sc = self.sc
+        second = bool(flags & 4)
+        if not self.use_graphs or sc._dense_pending > 0:
+            sc._gtvf_step_call(p, flags=flags, evaluated=second)
+            return
+        key = (flags, sc.parity, p.dt, p.flags)
+        g = self._graphs.get(key)
+        if g is None:
+            # (the kernels have all run eagerly by now: the dense evaluations)
+            parity, pending = sc.parity, sc._dense_pending
+            g = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream(sc.device)
+            side.wait_stream(torch.cuda.current_stream(sc.device))
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(g, stream=side):
+                    sc._gtvf_step_call(p, flags=flags, evaluated=False)
+            torch.cuda.current_stream(sc.device).wait_stream(side)
+            sc.parity, sc._dense_pending = parity, pending
+            self._graphs[key] = g
+        g.replay()
+        if second:
+            sc._evaluated()
+
     def gtvf_step(self, dt, nsteps=1, migrate_every=0):
         """GTVFIntegrator.one_timestep with the halo exchange between the
         re-pose (stage 2) and the force evaluation.  migrate_every = M > 0:
@@ -570,7 +603,7 @@ class SlabScene(object):
             # same for the payload); u, v, w and the boundary normals are
             # formed when somebody asks for them, as in DeviceScene.gtvf_step
             p = sc.params(dt)
-            sc._gtvf_step_call(p, flags=2, evaluated=False)
+            self._half(p, 2)
             # The rebuild decision is global (all_reduce MAX of the device
             # flag) and the host has to know it: it picks between the halo
             # refresh and a full exchange.  The refresh is right nine times
@@ -591,7 +624,7 @@ class SlabScene(object):
             self._flag_event.synchronize()
             if self._send_idx is None or int(self._flag_host[0]) != 0:
                 self.exchange_halo(full=True)
-            sc._gtvf_step_call(p, flags=4 | 1)
+            self._half(p, 4 | 1)
         if nsteps > 0:
             sc._particles_stale = True     # see DeviceScene.finalize_particles
         sc.steps_done += nsteps
