@@ -39,6 +39,10 @@ MU = float(os.environ.get('MGPU_MU', '0.0'))
 EXACT_STEPS = int(os.environ.get('MGPU_EXACT', '100000' if MU == 0.0 else '0'))
 LATERAL = float(os.environ.get('MGPU_LATERAL', '0'))
 MIGRATE = int(os.environ.get('MGPU_MIGRATE', '50' if LATERAL else '0'))
+# MGPU_ORACLE = n > 0: rank 0 also runs the CPU oracle (oracle/rbo.c, sparse
+# history) on the whole scene for the first n steps; the slab run must agree
+# with it too (frictionless: 1e-8 on xcm, R)
+ORACLE = int(os.environ.get('MGPU_ORACLE', '0'))
 
 
 def scene_of(arrays, info, dev):
@@ -67,9 +71,21 @@ def main():
     sc = scene_of(arrays, info, dev)
     slab = SlabScene(sc, rank, world)
     one = None
+    oarr = op = None
     if rank == 0:
         full, _, finfo = synthetic_pile(NB, slab=(0, world), span=world)
         one = scene_of(full, finfo, dev)
+        if ORACLE:
+            from oracle import rbo
+            oarr, _, oinfo = synthetic_pile(NB, slab=(0, world), span=world)
+            if LATERAL:
+                oarr[0].vcm[0::3] = LATERAL
+            # (torchrun exports OMP_NUM_THREADS=1)
+            rbo.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+            rbo.add_sparse_history(oarr[0], 8)
+            op = rbo.make_params(3, DT, 1e5, 1e3, MU, 0., -9.81, 0.,
+                                 eta_uniform=oinfo['eta_uniform'])
+    odone = 0
     ok = True
     seen_contact = False
     done = 0
@@ -115,6 +131,17 @@ def main():
                     [p_[name] for p_ in parts]).reshape(-1, s)
                 want = one.B[name].cpu().numpy()
                 errs[name] = float(np.abs(got - want).max())
+            if ORACLE and upto <= ORACLE:
+                from oracle import rbo
+                rbo.gtvf_step(oarr, ['body'], op, ks=8, nsteps=upto - odone)
+                odone = upto
+                for name, s_ in (('xcm', 3), ('R', 9)):
+                    got = np.empty(s_ * NB * world)
+                    got.reshape(-1, s_)[dem] = np.concatenate(
+                        [p_[name] for p_ in parts]).reshape(-1, s_)
+                    e = float(np.abs(got - oarr[0].constants[name]).max())
+                    errs['oracle_' + name] = e
+                    ok = ok and e < 1e-8
             cnt = one.read_counters(reset=True)
             print('mgpu_equiv world=%d%s bodies=%d step=%d active_slots/step='
                   '%.0f halo_bytes/step=%.0f migrated=%d bodies per rank %s '

@@ -26,8 +26,11 @@ def _run(port, **env):
     return out.stdout
 
 
-def test_two_rank_run_equals_single_rank():
-    _run(29517, MGPU_BODIES=600, MGPU_STEPS=700)
+def test_two_rank_run_equals_single_rank_and_oracle():
+    """... and, over the first 300 steps (contact from step ~250 on), the CPU
+    oracle run on the whole scene (1e-8 on xcm and R, frictionless)."""
+    out = _run(29517, MGPU_BODIES=600, MGPU_STEPS=700, MGPU_ORACLE=300)
+    assert 'oracle_xcm' in out
 
 
 def test_two_rank_run_with_migrating_bodies_equals_single_rank():
