@@ -129,6 +129,38 @@ __device__ __forceinline__ void rbx_point_velocity(const double *Rv, const doubl
   w = vc[2] + dw;
 }
 
+// ---- packed FP32 pairs --------------------------------------------------------
+// sm_100 has FFMA2 / FMUL2 / FADD2: one instruction, one issue slot, two
+// IEEE round-to-nearest FP32 operations on a 64-bit register pair (PTX
+// fma/mul/add.rn.f32x2).  Where the same arithmetic runs on two independent
+// values an issue-bound kernel needs half the FP32 instructions.  A pair is
+// carried as a 64-bit integer; ptxas folds rbx_f2(a, a) into a broadcast
+// operand and immediates into the instruction.
+typedef unsigned long long rbx_f2_t;
+__device__ __forceinline__ rbx_f2_t rbx_f2(float lo, float hi) {
+  rbx_f2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void rbx_f2_get(rbx_f2_t v, float &lo, float &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ rbx_f2_t rbx_f2_fma(rbx_f2_t a, rbx_f2_t b, rbx_f2_t c) {
+  rbx_f2_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ rbx_f2_t rbx_f2_mul(rbx_f2_t a, rbx_f2_t b) {
+  rbx_f2_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ rbx_f2_t rbx_f2_add(rbx_f2_t a, rbx_f2_t b) {
+  rbx_f2_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
 __device__ __forceinline__ void rbx_prefetch_l2(const void *p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }

@@ -1111,10 +1111,22 @@ k_slots(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
 #define RBX_FILTER_MINB 32
 #endif
 
+// Two list entries per iteration, their pair math in PACKED FP32 (FFMA2 /
+// FMUL2 / FADD2, rbx_common.cuh): the kernel is bound by instruction issue and
+// by the L1 lookups of its position gathers, and entries e, e + 1 of a list
+// run through identical arithmetic, so one instruction per operation serves
+// both.  A run may end at either entry of an iteration; both cases share ONE
+// closing block per iteration (the closing test at 3-6 active lanes was 35 %
+// of the executed instructions when every entry carried its own): a lane
+// whose run ends at the first entry keeps the second entry's weights out of
+// the sums (exact zeros), closes, and then opens the next run with that
+// entry.  Every operation is IEEE round-to-nearest in the order of the error
+// model above.  Lr and cu come as kernel arguments: formed in the kernel,
+// ptxas re-derives them from the FP64 parameters inside the closing block.
 template <int DIM, bool UNIFORM_H>
 __global__ void __launch_bounds__(32, RBX_FILTER_MINB)
 k_filter(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P,
-         float h_uniform) {
+         float h_uniform, float Lr, float cu) {
   const int lane = threadIdx.x;
   const size_t n_rigid = (size_t)S.n_rigid;
   const float4 *__restrict__ pos = reinterpret_cast<const float4 *>(S.pos32);
@@ -1129,8 +1141,6 @@ k_filter(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P
   const bool dense_out = !S.alist_out || (P.flags & RBX_PARAM_DENSE_OUT);
   constexpr float kU = 5.9604645e-8f;            // 2^-24
   constexpr float kSqrt3 = 1.7320509f;
-  const float Lr = (float)((P.reach + P.skin) * (1. + 1e-6));
-  const float cu = (float)(S.list_cap + 16) * kU;
   const float sigma = DIM == 2 ? (float)(0.31830988618379067154 * 7.0 / 478.0)
                                : (float)(0.31830988618379067154 / 120.0);
 
@@ -1160,49 +1170,109 @@ k_filter(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P
       const float eu = ex + er;
       const float s0f = s0 * 1.0001f;
       // uniform h: constants of the kernel
-      float h1 = 0.f, Th = 0.f, T = 0.f, dfloor = 0.f;
+      rbx_f2_t H1 = 0ull, TH = 0ull, TT = 0ull, DF = 0ull;
       if (UNIFORM_H) {
-        h1 = 1.f / (0.5f * (me.w + h_uniform));
-        T = vol * sigma * (DIM == 2 ? h1 * h1 : h1 * h1 * h1);
-        Th = T * h1;
+        const float h1 = 1.f / (0.5f * (me.w + h_uniform));
+        const float T = vol * sigma * (DIM == 2 ? h1 * h1 : h1 * h1 * h1);
         const float dq = er * h1;
-        dfloor = 1.5e5f * (dq * dq) * (dq * dq);
+        const float dfloor = 1.5e5f * (dq * dq) * (dq * dq);
+        H1 = rbx_f2(h1, h1); TT = rbx_f2(T, T); TH = rbx_f2(T * h1, T * h1);
+        DF = rbx_f2(dfloor, dfloor);
       }
 
+      // sums of the open run
       float ax = 0.f, ay = 0.f, az = 0.f, w1 = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
       float wA = 0.f, SD = 0.f;
-      int run = 0;
-      int ecur = 0, estart = 0;        // entry being read, first entry of its run
+      int run = 0, estart = 0;
 
-      auto entry = [&](int qc, const float4 sp) {
-        const float dx = me.x - sp.x, dy = me.y - sp.y, dz = me.z - sp.z;
-        const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-        float rinv;
-        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(r2));
-        const float r = r2 * rinv;
+      const int *cl = S.nbr_srt + t;
+      int qa = nlist > 0 ? cl[0] : 0;
+      int qb = nlist > 1 ? cl[n_rigid] : 0;
+      int la = nlist > 2 ? cl[2 * n_rigid] : 0;
+      int lb = nlist > 3 ? cl[3 * n_rigid] : 0;
+      cl += 4 * n_rigid;
+      float4 sa = gather(qa), sb = gather(qb);
+      for (int e0 = 0; e0 < nlist; e0 += 2) {
+        const rbx_f2_t dx = rbx_f2(me.x - sa.x, me.x - sb.x);
+        const rbx_f2_t dy = rbx_f2(me.y - sa.y, me.y - sb.y);
+        const rbx_f2_t dz = rbx_f2(me.z - sa.z, me.z - sb.z);
         if (!UNIFORM_H) {
-          float hij = 0.5f * (me.w + sp.w);
-          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(h1) : "f"(hij));
-          T = vol * sigma * (DIM == 2 ? h1 * h1 : h1 * h1 * h1);
-          Th = T * h1;
-          const float dq = er * h1;
-          dfloor = 1.5e5f * (dq * dq) * (dq * dq);
+          float ha, hb;
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ha) : "f"(0.5f * (me.w + sa.w)));
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(hb) : "f"(0.5f * (me.w + sb.w)));
+          H1 = rbx_f2(ha, hb);
+          const rbx_f2_t vs = rbx_f2(vol * sigma, vol * sigma);
+          TT = rbx_f2_mul(vs, DIM == 2 ? rbx_f2_mul(H1, H1) : rbx_f2_mul(rbx_f2_mul(H1, H1), H1));
+          TH = rbx_f2_mul(TT, H1);
+          const rbx_f2_t dq = rbx_f2_mul(rbx_f2(er, er), H1);
+          const rbx_f2_t dq2 = rbx_f2_mul(dq, dq);
+          DF = rbx_f2_mul(rbx_f2_mul(rbx_f2(1.5e5f, 1.5e5f), dq2), dq2);
         }
-        const float q = r * h1;
-        const float t3 = fmaxf(3.f - q, 0.f), t2 = fmaxf(2.f - q, 0.f), t1 = fmaxf(1.f - q, 0.f);
-        const float a3 = t3 * t3, a2 = t2 * t2, a1 = t1 * t1;
-        const float b3 = a3 * a3, b2 = a2 * a2, b1 = a1 * a1;
-        const float wv = fmaf(15.f, b1 * t1, fmaf(-6.f, b2 * t2, b3 * t3));
-        const float Dq = fmaf(100.5f, b1, fmaf(40.2f, b2, fmaf(6.7f, b3, dfloor)));
-        const float tmp2 = T * wv;
-        const float tmp1 = tmp2 * rinv;
-        ax = fmaf(dx, tmp1, ax); ay = fmaf(dy, tmp1, ay); az = fmaf(dz, tmp1, az);
-        bx = fmaf(dx, tmp2, bx); by = fmaf(dy, tmp2, by); bz = fmaf(dz, tmp2, bz);
-        w1 += tmp2;
-        wA += tmp1;
-        SD = fmaf(Th, Dq, SD);
-        if (t3 > 0.f) npairs++;
-        if (qc < 0) {                              // last entry of a source body
+        // software pipeline: positions of the next two entries, list entries
+        // of the two after them
+        const int qa_now = qa, qb_now = qb;
+        sa = gather(la); sb = gather(lb);
+        qa = la; qb = lb;
+        la = (e0 + 4 < nlist) ? cl[0] : 0;
+        lb = (e0 + 5 < nlist) ? cl[n_rigid] : 0;
+        cl += 2 * n_rigid;
+
+        const rbx_f2_t r2 = rbx_f2_fma(dz, dz, rbx_f2_fma(dy, dy, rbx_f2_mul(dx, dx)));
+        float r2a, r2b, ia, ib;
+        rbx_f2_get(r2, r2a, r2b);
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(ia) : "f"(r2a));
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(ib) : "f"(r2b));
+        const rbx_f2_t rinv = rbx_f2(ia, ib);
+        const rbx_f2_t q = rbx_f2_mul(rbx_f2_mul(r2, rinv), H1);
+        const rbx_f2_t mone = rbx_f2(-1.f, -1.f);
+        float lo, hi;
+        rbx_f2_get(rbx_f2_fma(q, mone, rbx_f2(3.f, 3.f)), lo, hi);
+        const float t3a = fmaxf(lo, 0.f), t3b = fmaxf(hi, 0.f);
+        const rbx_f2_t t3 = rbx_f2(t3a, t3b);
+        rbx_f2_get(rbx_f2_fma(q, mone, rbx_f2(2.f, 2.f)), lo, hi);
+        const rbx_f2_t t2 = rbx_f2(fmaxf(lo, 0.f), fmaxf(hi, 0.f));
+        rbx_f2_get(rbx_f2_fma(q, mone, rbx_f2(1.f, 1.f)), lo, hi);
+        const rbx_f2_t t1 = rbx_f2(fmaxf(lo, 0.f), fmaxf(hi, 0.f));
+        const rbx_f2_t a3 = rbx_f2_mul(t3, t3), a2 = rbx_f2_mul(t2, t2), a1 = rbx_f2_mul(t1, t1);
+        const rbx_f2_t b3 = rbx_f2_mul(a3, a3), b2 = rbx_f2_mul(a2, a2), b1 = rbx_f2_mul(a1, a1);
+        const rbx_f2_t wv = rbx_f2_fma(rbx_f2(15.f, 15.f), rbx_f2_mul(b1, t1),
+                                       rbx_f2_fma(rbx_f2(-6.f, -6.f), rbx_f2_mul(b2, t2),
+                                                  rbx_f2_mul(b3, t3)));
+        const rbx_f2_t Dq = rbx_f2_fma(rbx_f2(100.5f, 100.5f), b1,
+                                       rbx_f2_fma(rbx_f2(40.2f, 40.2f), b2,
+                                                  rbx_f2_fma(rbx_f2(6.7f, 6.7f), b3, DF)));
+        const rbx_f2_t tmp2 = rbx_f2_mul(TT, wv);
+        const rbx_f2_t tmp1 = rbx_f2_mul(tmp2, rinv);
+        const rbx_f2_t sd = rbx_f2_mul(TH, Dq);
+
+        const bool bvalid = e0 + 1 < nlist;
+        const bool ca = qa_now < 0;            // the open run ends at entry e0
+        const bool cb = qb_now < 0;            // ... or at e0 + 1 (0 when absent)
+        if (t3a > 0.f) npairs++;
+        if (t3b > 0.f && bvalid) npairs++;
+        // weights of the second entry: out of the packed sums when it belongs
+        // to the next run (or does not exist: then ca holds, the last entry
+        // of a list always closes a run)
+        float w1a, w1b, w2a, w2b, sda, sdb, dxa, dxb, dya, dyb, dza, dzb;
+        rbx_f2_get(tmp1, w1a, w1b);
+        rbx_f2_get(tmp2, w2a, w2b);
+        rbx_f2_get(sd, sda, sdb);
+        rbx_f2_get(dx, dxa, dxb); rbx_f2_get(dy, dya, dyb); rbx_f2_get(dz, dza, dzb);
+        ax = fmaf(dxa, w1a, ax); ay = fmaf(dya, w1a, ay); az = fmaf(dza, w1a, az);
+        bx = fmaf(dxa, w2a, bx); by = fmaf(dya, w2a, by); bz = fmaf(dza, w2a, bz);
+        w1 += w2a; wA += w1a; SD += sda;
+        {
+          const float u1 = ca ? 0.f : w1b, u2 = ca ? 0.f : w2b, us = ca ? 0.f : sdb;
+          ax = fmaf(dxb, u1, ax); ay = fmaf(dyb, u1, ay); az = fmaf(dzb, u1, az);
+          bx = fmaf(dxb, u2, bx); by = fmaf(dyb, u2, by); bz = fmaf(dzb, u2, bz);
+          w1 += u2; wA += u1; SD += us;
+        }
+
+        bool pend = ca || cb;
+        bool redo = ca && bvalid;              // the second entry opens the next run
+        int ecur = ca ? e0 : e0 + 1;
+#pragma unroll 1
+        while (pend) {                         // last entry of a source body
           const float dw = fmaf(er, SD, cu * w1);
           const float dA = kSqrt3 * fmaf(eu, wA, dw);
           const float dB = kSqrt3 * fmaf(ex, w1, Lr * dw);
@@ -1222,38 +1292,25 @@ k_filter(const __grid_constant__ RbxScene S, const __grid_constant__ RbxParams P
           // w <= 1e-12: the slot has no normal, dist = 0, overlap == spacing0
           const bool drop = (wh < 0.99e-12f) || (lhs > 0.f && lhs > rhs);
           if (!drop || all) {
-            // the exact pass starts at the first kept run and stops after
-            // the last one
             if (mask == 0u) { efirst = estart; rfirst = run < 31 ? run : 31; }
             elast = ecur;
             mask |= 1u << (run < 31 ? run : 31);
           }
           run++;
           estart = ecur + 1;
+          // the next run starts empty, or with the second entry of this
+          // iteration
           ax = ay = az = w1 = bx = by = bz = 0.f;
           wA = SD = 0.f;
+          if (redo) {
+            ax = dxb * w1b; ay = dyb * w1b; az = dzb * w1b;
+            bx = dxb * w2b; by = dyb * w2b; bz = dzb * w2b;
+            w1 = w2b; wA = w1b; SD = sdb;
+          }
+          pend = redo && cb;
+          redo = false;
+          ecur = e0 + 1;
         }
-      };
-
-      // software pipeline: the list entries of the next pair of entries are
-      // in flight while the positions of this one are gathered
-      const int *cl = S.nbr_srt + t;
-      int qa = nlist > 0 ? cl[0] : 0;
-      int qb = nlist > 1 ? cl[n_rigid] : 0;
-      int la = nlist > 2 ? cl[2 * n_rigid] : 0;
-      int lb = nlist > 3 ? cl[3 * n_rigid] : 0;
-      cl += 4 * n_rigid;
-      float4 sa = gather(qa), sb = gather(qb);
-      for (int e0 = 0; e0 < nlist; e0 += 2) {
-        const float4 ga = gather(la), gb = gather(lb);
-        const int na = (e0 + 4 < nlist) ? cl[0] : 0;
-        const int nb = (e0 + 5 < nlist) ? cl[n_rigid] : 0;
-        cl += 2 * n_rigid;
-        ecur = e0;
-        entry(qa, sa);
-        ecur = e0 + 1;
-        if (e0 + 1 < nlist) entry(qb, sb);
-        qa = la; qb = lb; sa = ga; sb = gb; la = na; lb = nb;
       }
       if (mask == 0u && dense_out) {
         // nothing can be in contact: BodyForce alone (:122-125), no history
@@ -1401,12 +1458,14 @@ extern "C" int rbx_contact_slots(const RbxScene *scene, const RbxCells *cells,
     const int resf = sms * RBX_FILTER_MINB - 1;
     if (nf > resf) nf = resf;
     const float hu = (float)params->h_uniform;
+    const float f_lr = (float)((params->reach + params->skin) * (1. + 1e-6));
+    const float f_cu = (float)(scene->list_cap + 16) * 5.9604645e-8f;
     if (scene->dim == 3) {
-      if (uni) k_filter<3, true><<<nf, 32, 0, st>>>(*scene, *params, hu);
-      else k_filter<3, false><<<nf, 32, 0, st>>>(*scene, *params, 0.f);
+      if (uni) k_filter<3, true><<<nf, 32, 0, st>>>(*scene, *params, hu, f_lr, f_cu);
+      else k_filter<3, false><<<nf, 32, 0, st>>>(*scene, *params, 0.f, f_lr, f_cu);
     } else {
-      if (uni) k_filter<2, true><<<nf, 32, 0, st>>>(*scene, *params, hu);
-      else k_filter<2, false><<<nf, 32, 0, st>>>(*scene, *params, 0.f);
+      if (uni) k_filter<2, true><<<nf, 32, 0, st>>>(*scene, *params, hu, f_lr, f_cu);
+      else k_filter<2, false><<<nf, 32, 0, st>>>(*scene, *params, 0.f, f_lr, f_cu);
     }
     // exact pass: over the compact list, or over every particle when the
     // list has grown past 1/8 of them (see k_slots)
