@@ -364,15 +364,18 @@ def main():
     roof = {'bound': 'hbm',
             'kernel': 'contact evaluation on reused neighbour lists '
             '(rbx_contact_slots: k_sparse_reset, k_filter = FP32 first pass '
-            'over every list entry, k_slots = exact FP64 pass over what it '
-            'could not exclude)',
+            'over every list entry (FFMA2 / FMUL2, two entries per '
+            'instruction), k_slots = exact FP64 pass over what it could not '
+            'exclude)',
             'achieved': contact_b / (contact_ms * 1e-3) / 1e9, 'peak': peak,
             'unit': 'GB/s', 'peak_source': peak_src, 'traffic': traffic,
             'traffic_source': 'profiles/r02_traffic.json (ncu dram__bytes '
             'read+write of k_filter + k_slots, one evaluation)'
             if traffic else None,
-            'secondary_limiter': ('instruction issue (FP32 pair math over '
-                                  '%.3g list entries per step), not HBM; '
+            'secondary_limiter': ('instruction issue and the latency of the '
+                                  '16-byte position gathers (packed-FP32 '
+                                  'pair math over %.3g list entries per '
+                                  'step), not HBM; '
                                   'ncu, profiles/r02_traffic.json: ' %
                                   list_entries + limiter)
             if limiter else None,

@@ -11,6 +11,14 @@ import subprocess
 import sys
 
 
+def _num(v):
+    # (lines without a count show '-' or an empty cell)
+    try:
+        return int(v)
+    except ValueError:
+        return 0
+
+
 def lines(rep, kernel, launch=0):
     out = subprocess.run(
         ['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source',
@@ -31,9 +39,9 @@ def lines(rep, kernel, launch=0):
         elif hdr and len(r) > 5 and r[0] != '':
             key = (fname, int(r[0]))
             e = res.setdefault(key, [r[1], 0, 0, 0])
-            e[1] += int(r[ci] or 0)
-            e[2] += int(r[ct] or 0)
-            e[3] += int(r[cs] or 0)
+            e[1] += _num(r[ci])
+            e[2] += _num(r[ct])
+            e[3] += _num(r[cs])
     return res
 
 
