@@ -588,7 +588,11 @@ def main():
                 'stepper': 'GTVF', 'ks': args.ks,
                 'skin_factor': solver.skin_factor if world == 1 or strong
                 else 0.075,
-                'graph': world == 1},
+                # one graph per step on one GPU; slabs replay the two halves
+                # of the step around the halo exchange as graphs
+                'graph': True if world == 1 else (
+                    'two graphs per step, the halo exchange between them'
+                    if getattr(slab, 'use_graphs', False) else False)},
             'contact_pairs_per_s': pairs_per_s,
             'contact_pairs_per_step': tot_pairs / args.steps,
             'active_slots_per_step': tot_active / args.steps,
