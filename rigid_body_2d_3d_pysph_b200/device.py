@@ -761,25 +761,35 @@ class DeviceScene(object):
 
     def _run_graph(self, p, nsteps):
         """Two steps (one history ping-pong period) captured as a CUDA graph:
-        small scenes are launch-bound (about a dozen launches per step)."""
-        key = (p.dt, self.parity)
-        if self._graph is None or self._graph[0] != key:
+        small scenes are launch-bound (about a dozen launches per step).  A
+        graph is bound to the history buffer its first step reads, so both
+        are captured at the first use -- capturing executes nothing -- and a
+        later call that starts on the other buffer (an odd number of steps
+        in between) replays at once instead of capturing in the middle of
+        somebody's timed loop."""
+        if self._graph is None or self._graph[0] != p.dt:
             start = self.parity
-            g = torch.cuda.CUDAGraph()
+            cur = torch.cuda.current_stream(self.device)
             s = torch.cuda.Stream(self.device)
-            s.wait_stream(torch.cuda.current_stream(self.device))
+            s.wait_stream(cur)
+            graphs = {}
             with torch.cuda.stream(s):
                 self._gtvf_step_call(p, 1)     # warm-up outside capture
                 self._gtvf_step_call(p, 1)
                 s.synchronize()
-                with torch.cuda.graph(g, stream=s):
-                    self._gtvf_step_call(p, 1)
-                    self._gtvf_step_call(p, 1)
-            torch.cuda.current_stream(self.device).wait_stream(s)
-            assert self.parity == start
-            self._graph = (key, g)
+                for q in (start, start ^ 1):
+                    self.parity = q
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=s):
+                        self._gtvf_step_call(p, 1)
+                        self._gtvf_step_call(p, 1)
+                    assert self.parity == q
+                    graphs[q] = g
+                self.parity = start
+            cur.wait_stream(s)
+            self._graph = (p.dt, graphs)
             nsteps -= 2
-        g = self._graph[1]
+        g = self._graph[1][self.parity]
         while nsteps >= 2:
             g.replay()
             nsteps -= 2
