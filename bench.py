@@ -50,6 +50,31 @@ def note(msg):
     sys.stderr.flush()
 
 
+def claim_stdout():
+    """stdout carries ONE JSON line.  Native libraries write to file
+    descriptor 1 behind Python's back (NCCL prints its version banner there,
+    and everything NCCL_DEBUG asks for): from here on descriptor 1 is stderr,
+    and the returned descriptor is the real stdout for emit()."""
+    try:
+        sys.stdout.flush()
+        real = os.dup(1)
+        os.dup2(2, 1)
+        return real
+    except OSError:
+        return None
+
+
+def emit(real, text):
+    """the JSON line, to the real stdout"""
+    if real is None:
+        print(text)
+        sys.stdout.flush()
+        return
+    data = (text + '\n').encode()
+    while data:
+        data = data[os.write(real, data):]
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
@@ -232,6 +257,7 @@ def main():
         run_reference(args, rank, world)
         return
 
+    out_fd = claim_stdout()
     import torch
     import torch.distributed as dist
     from rigid_body_2d_3d_pysph_b200 import _lib
@@ -604,7 +630,7 @@ def main():
             'scene_build_s': t_build,
         }
         line.update(extras)
-        print(json.dumps(line))
+        emit(out_fd, json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 

@@ -44,3 +44,18 @@ def test_b200_arm_needs_a_gpu():
                '0', '--no-cpu')
     assert out.returncode != 0
     assert not [ln for ln in out.stdout.splitlines() if ln.startswith('{')]
+
+
+def test_stdout_carries_only_the_json_line():
+    """Native libraries print to file descriptor 1 (the NCCL version banner
+    at N > 1): bench.py moves descriptor 1 to stderr and writes its one JSON
+    line to the real stdout."""
+    code = ('import os, sys; sys.path.insert(0, %r); import bench; '
+            'fd = bench.claim_stdout(); os.write(1, b"NCCL version x\\n"); '
+            'print("python noise"); sys.stdout.flush(); '
+            'bench.emit(fd, \'{"a": 1}\')' % ROOT)
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True,
+                       text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == '{"a": 1}\n'
+    assert 'NCCL version x' in r.stderr and 'python noise' in r.stderr
